@@ -1,0 +1,39 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    """The C restatement of the reference hot path (test infrastructure)."""
+    from oracle import Oracle
+
+    return Oracle()
+
+
+@pytest.fixture(scope="session")
+def refhost():
+    """The unmodified reference compiled as host C++; skipped where oracle/_ref is absent."""
+    from oracle import RefHost
+
+    if not RefHost.available():
+        pytest.skip("oracle/_ref/libref_host.so not built (needs /root/reference)")
+    return RefHost()
+
+
+@pytest.fixture(scope="session")
+def golden():
+    import numpy as np
+
+    return {n: np.load(os.path.join(GOLDEN, n + ".npz")) for n in ("scene", "exponent", "bake", "frames", "shade")}
