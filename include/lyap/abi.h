@@ -1,0 +1,169 @@
+/*
+ * lyap/abi.h -- C ABI of liblyap_b200.so: the drop-in boundary for the reference's
+ * hot path (the two __global__ kernels of kernel.hpp:17,19 and the host helpers of
+ * scene.hpp:11-15 / params.hpp:26 that feed them).
+ *
+ * Plain pointers and sizes only; no torch, no C++ types.  Every entry point that
+ * touches the GPU returns 0 on success or a cudaError_t / LYAP_ERR_* code and never
+ * calls exit() (the reference's checkCudaErrors does, helper_cuda.h).  Device entry
+ * points are stream-ordered and do not synchronise; `stream` is a cudaStream_t
+ * passed as void* (NULL = the legacy default stream, as in the reference).
+ *
+ * INTEGRATION.md shows the two-line change in lyap_interactive.cu / lyap_calculate.cu.
+ */
+#ifndef LYAP_ABI_H
+#define LYAP_ABI_H
+
+#include "lyap/types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* How the per-sample exponent is evaluated. */
+enum lyap_mode {
+    /* Parity mode against the reference's CUDA build: the same PTX-level operations
+     * in the same order as `nvcc --use_fast_math kernel.cu` (GNUmakefile:8), one
+     * lg2.approx per step.  Bit-identical LyapPoint/RGBA to the reference kernel on
+     * the same GPU.  SFU-bound. */
+    LYAP_MODE_EXACT = 0,
+    /* Throughput mode: derivative magnitudes are multiplied, the exponent folded out
+     * with integer ops, log taken once per sample.  Same chaotic trajectory, bake
+     * within 1e-3; images differ where the reference's jitter PRNG decorrelates. */
+    LYAP_MODE_FAST = 1,
+    /* Parity mode against the reference's HOST build (and the CPU oracle): IEEE
+     * arithmetic without contraction and a bit-exact glibc logf per step. */
+    LYAP_MODE_HOST = 2,
+};
+
+enum lyap_dtype { LYAP_F32 = 0, LYAP_F16 = 1 };
+
+enum lyap_error {
+    LYAP_OK = 0,
+    LYAP_ERR_BAD_SEQUENCE = 10001,   /* empty, symbol outside 0..3, or longer than LYAP_MAX_SEQUENCE */
+    LYAP_ERR_BAD_ARGUMENT = 10002,
+    LYAP_ERR_NO_DEVICE = 10003,
+    LYAP_ERR_IO = 10004,
+};
+
+enum { LYAP_MAX_SEQUENCE = 1024 };
+
+const char *lyap_version(void);
+const char *lyap_error_string(int code);
+
+/* Tuning / test knobs: "render_warps_per_sm" (persistent warps per SM, default 16),
+ * "bake_blocks_per_sm" (cap; 0 = occupancy maximum), "force_generic" (1 = always use
+ * the per-step-select exponent loop instead of a period instantiation). */
+int lyap_set_option(const char *key, long value);
+/* Which unrolled-period instantiation a sequence runs on: its period's smallest
+ * compiled multiple, 0 for the generic loop, -1 for an invalid sequence. */
+int lyap_plan_period(const int32_t *seq, uint32_t settle, uint32_t accum);
+
+/* ----------------------------------------------------------------------------
+ * Host scene helpers -- same meaning as the reference functions they replace.
+ * ------------------------------------------------------------------------- */
+
+/* params_init() (params.cu:21-114): the hard-coded defaults.  The reference fills
+ * globals; here the caller passes the objects.  `lights` must hold LYAP_MAX_LIGHTS
+ * entries; `sequence` receives the NUL-terminated default string ("BCABA"). */
+void lyap_params_init(lyap_params *prm, lyap_cam *cam, lyap_light *lights, uint32_t *num_lights,
+                      char *sequence, size_t sequence_cap, uint32_t *image_width, uint32_t *image_height);
+
+/* scene_convert_sequence() (scene.cu:69-108): "A6B6C6" -> malloc'd int array ending
+ * in -1, returns the element count including the terminator; caller free()s.  A bad
+ * letter returns 0 with *seqP = NULL instead of exit(1). */
+size_t lyap_scene_convert_sequence(int32_t **seqP, const unsigned char *seqStr);
+
+/* scene_cam_recalculate() (scene.cu:31-63) and scene_lights_recalculate() (:20-29). */
+void lyap_scene_cam_recalculate(lyap_cam *camP, uint32_t tw, uint32_t th, uint32_t td);
+void lyap_scene_lights_recalculate(lyap_light *lights, size_t num_lights);
+
+/* scale.pl:5-11 and the camera block scale.pl:33-48 / params.cu:42-57 as a runtime
+ * function: sets cam->C and cam->Q for eased path position i in [0,1]. */
+double lyap_ease_in_out_quart(double t, double b, double c, double d);
+void lyap_campath_orbit(double i, lyap_cam *cam);
+/* Frame f of an n-frame orbit: t = f/(n-1), i = ease(t); i is rounded to 15
+ * significant digits as scale.pl's string interpolation does. */
+void lyap_campath_frame(uint32_t f, uint32_t n_frames, lyap_cam *cam);
+
+/* ----------------------------------------------------------------------------
+ * Device entry points (caller-owned device buffers, as in the reference).
+ * ------------------------------------------------------------------------- */
+
+/* Replaces  kernel_calc_render<<<blocks,threads>>>(cudaRGBA, cudaPoints, cam, prm,
+ *           cudaSeq, cudaLights, num_lights)            (lyap_interactive.cu:711).
+ *
+ * d_rgba / d_points: width*height elements, row-major, index x + y*width.
+ * seq: the HOST array scene_convert_sequence produced (the reference uploads it to
+ *      cudaSeq; this library reads it on the host and bakes it into the launch).
+ * d_lights: device array of num_lights lights, already recalculated.
+ * Miss pixels leave d_points[ind] untouched and shade whatever it holds, exactly as
+ * the reference does (kernel.cu:508-512): zero-fill it for defined output.
+ * d_evals: optional device counter; the number of exponent evaluations is added. */
+int lyap_render(lyap_rgba *d_rgba, lyap_point *d_points, const lyap_cam *cam, const lyap_params *prm,
+                const int32_t *seq, const lyap_light *d_lights, uint32_t num_lights,
+                uint32_t width, uint32_t height, int mode, unsigned long long *d_evals, void *stream);
+
+/* The same frame cut into tile x tile pixel tiles, dealt round-robin to `world`
+ * ranks; this call renders rank `rank`'s tiles only.  With compact != 0 the outputs
+ * are written densely in the rank's work order (lyap_tile_count() elements) instead
+ * of at their image positions. */
+int lyap_render_tiles(lyap_rgba *d_rgba, lyap_point *d_points, const lyap_cam *cam, const lyap_params *prm,
+                      const int32_t *seq, const lyap_light *d_lights, uint32_t num_lights,
+                      uint32_t width, uint32_t height, uint32_t tile, uint32_t rank, uint32_t world,
+                      int compact, int mode, unsigned long long *d_evals, void *stream);
+/* Number of work items (tile pixels, including padding of ragged edge tiles) of a rank. */
+uint64_t lyap_tile_count(uint32_t width, uint32_t height, uint32_t tile, uint32_t rank, uint32_t world);
+/* Rank 0: place a rank's compact buffer (elem_size bytes per item) into the full image. */
+int lyap_scatter_tiles(void *d_image, const void *d_compact, uint32_t elem_size, uint32_t width, uint32_t height,
+                       uint32_t tile, uint32_t rank, uint32_t world, void *stream);
+
+/* Re-shade a stored LyapPoint buffer without marching (lights/camera edits). */
+int lyap_shade_points(lyap_rgba *d_rgba, const lyap_point *d_points, const lyap_cam *cam,
+                      const lyap_light *d_lights, uint32_t num_lights, uint64_t count, int mode, void *stream);
+
+/* Replaces  kernel_calc_volume<<<blocks,threads>>>(cudaExps, prm, cudaSeq)
+ *                                                       (lyap_calculate.cu:72).
+ * Voxel (x,y,z) samples (4x/nx, 4y/ny, 4z/nz) (kernel.cu:527-529) and is stored at
+ * x + (y + z*ny)*nx of the FULL volume d_exps; this call fills planes z0 <= z < z1. */
+int lyap_bake(void *d_exps, int dtype, const lyap_params *prm, const int32_t *seq,
+              uint32_t nx, uint32_t ny, uint32_t nz, uint32_t z0, uint32_t z1, int mode, void *stream);
+
+/* Exponent at arbitrary points (xyz: n*3 floats on the device) -> d_out[n]. */
+int lyap_exponent_points(float *d_out, const float *d_xyz, uint64_t n, const lyap_params *prm,
+                         const int32_t *seq, int mode, void *stream);
+
+/* ----------------------------------------------------------------------------
+ * Whole-call convenience with HOST buffers (allocations, copies and the final
+ * synchronise happen inside; this is the end-to-end path bench.py times).
+ * ------------------------------------------------------------------------- */
+int lyap_render_host(lyap_rgba *h_rgba, lyap_point *h_points /* may be NULL */, const lyap_cam *cam,
+                     const lyap_params *prm, const int32_t *seq, const lyap_light *h_lights, uint32_t num_lights,
+                     uint32_t width, uint32_t height, int mode, int device, unsigned long long *evals_out);
+int lyap_bake_host(void *h_exps, int dtype, const lyap_params *prm, const int32_t *seq,
+                   uint32_t nx, uint32_t ny, uint32_t nz, uint32_t z0, uint32_t z1, int mode, int device);
+
+/* ----------------------------------------------------------------------------
+ * Headless output in the reference's formats.
+ * ------------------------------------------------------------------------- */
+/* ASCII "P3" exactly as save_ppm writes it (lyap_interactive.cu:595-606). */
+int lyap_write_ppm(const char *path, const lyap_rgba *h_rgba, uint32_t width, uint32_t height);
+/* 8-bit RGB PNG (zlib deflate). */
+int lyap_write_png(const char *path, const lyap_rgba *h_rgba, uint32_t width, uint32_t height);
+/* Raw dumps: LyapPoint[] (save_points, :642-647) and exps.raw (lyap_calculate.cu:84-86). */
+int lyap_write_raw(const char *path, const void *data, uint64_t bytes);
+/* The reference's self-describing file stem (lyap_interactive.cu:577-590), without extension. */
+int lyap_format_filename(char *out, size_t cap, const char *prefix, unsigned long timestamp, uint32_t width, uint32_t height,
+                         const char *sequence, const lyap_cam *cam, const lyap_params *prm);
+
+/* ----------------------------------------------------------------------------
+ * Roofline probes: register-only FFMA and MUFU.LG2 loops.  Returns achieved
+ * lane-operations per second over `iters` inner iterations on the current device.
+ * ------------------------------------------------------------------------- */
+int lyap_probe_peaks(double *ffma_lane_ops_per_s, double *mufu_lane_ops_per_s, double *sm_clock_hz_est, int *sm_count);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* LYAP_ABI_H */

@@ -1,0 +1,401 @@
+// abi.cu -- the extern "C" GPU entry points of include/lyap/abi.h.
+//
+// Host-side work per call: validate, turn the reference's -1-terminated sequence into
+// a SeqPlan (iteration schedule + which period instantiation to launch), size a
+// persistent grid from the SM count and the kernel's occupancy, launch on the
+// caller's stream.  No synchronisation, no allocation on the device entry points
+// apart from a once-per-device scratch block of work-queue counters.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "kernels/launch.hpp"
+#include "lyap/abi.h"
+
+using namespace lyap;
+
+namespace {
+
+// ------------------------------------------------------------------ options
+std::atomic<long> g_force_generic{0};
+std::atomic<long> g_render_warps_per_sm{0};   // 0 = default
+std::atomic<long> g_bake_blocks_per_sm{0};    // 0 = occupancy maximum
+
+constexpr int kDefaultRenderWarpsPerSM = 16;
+
+// ---------------------------------------------------------------- sequence plan
+const int kPeriods[] = {
+#define X(p) p,
+    LYAP_PERIODS(X)
+#undef X
+};
+
+int pick_period(uint32_t len)
+{
+    if (g_force_generic.load()) return 0;
+    int best = 0;
+    for (int p : kPeriods)
+        if (p > 0 && (uint32_t)p % len == 0 && (best == 0 || p < best)) best = p;
+    return best;
+}
+
+// Builds the plan; returns the period instantiation to launch (0 = generic) or -1.
+int build_plan(SeqPlan &sp, const int32_t *seq, uint32_t settle, uint32_t accum)
+{
+    if (!seq) return -1;
+    uint32_t len = 0;
+    while (seq[len] != -1) {
+        if (seq[len] < 0 || seq[len] > 3) return -1;
+        if (++len > LYAP_MAX_SEQUENCE) return -1;
+    }
+    if (len == 0) return -1;
+    // the shortest period that generates the same infinite symbol stream
+    uint32_t per = len;
+    for (uint32_t p = 1; p < len; ++p) {
+        if (len % p) continue;
+        bool ok = true;
+        for (uint32_t i = p; i < len && ok; ++i) ok = seq[i] == seq[i - p];
+        if (ok) { per = p; break; }
+    }
+    const int P = pick_period(per);
+    const uint32_t L = P > 0 ? (uint32_t)P : per;
+    memset(&sp, 0, sizeof sp);
+    sp.len = L;
+    sp.settle = settle;
+    sp.accum = accum;
+    for (uint32_t i = 0; i < L; ++i) sp.sym[i] = (uint8_t)seq[i % per];
+    sp.settle_head = settle % L;
+    sp.settle_periods = settle / L;
+    sp.accum_periods = accum / L;
+    sp.accum_tail = accum % L;
+    for (uint32_t k = 0; k < L && k < (uint32_t)kMaxPeriodRegs; ++k) sp.rot[k] = sp.sym[(sp.settle_head + k) % L];
+    // symbol census over the accumulate steps (positions settle .. settle+accum-1)
+    uint32_t per_period[4] = {0, 0, 0, 0};
+    for (uint32_t i = 0; i < L; ++i) per_period[sp.sym[i]]++;
+    for (int s = 0; s < 4; ++s) sp.cnt[s] = per_period[s] * sp.accum_periods;
+    for (uint32_t k = 0; k < sp.accum_tail; ++k) sp.cnt[sp.sym[(sp.settle_head + k) % L]]++;
+    return P;
+}
+
+// ------------------------------------------------------------ per-device scratch
+struct DeviceScratch {
+    int sm_count = 0;
+    unsigned long long *counters = nullptr;   // ring of work-queue heads
+    std::atomic<unsigned> next{0};
+};
+constexpr unsigned kCounterRing = 4096;
+std::mutex g_mu;
+DeviceScratch *g_scratch[64] = {};
+
+cudaError_t scratch_for_current_device(DeviceScratch **out)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (!g_scratch[dev]) {
+        DeviceScratch *s = new DeviceScratch;
+        if ((e = cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) { delete s; return e; }
+        if ((e = cudaMalloc(&s->counters, sizeof(unsigned long long) * kCounterRing)) != cudaSuccess) { delete s; return e; }
+        if ((e = cudaMemset(s->counters, 0, sizeof(unsigned long long) * kCounterRing)) != cudaSuccess) { delete s; return e; }
+        g_scratch[dev] = s;
+    }
+    *out = g_scratch[dev];
+    return cudaSuccess;
+}
+
+template <class F1, class F2, class F3>
+auto by_mode(int mode, F1 exact, F2 fast, F3 host) -> decltype(exact())
+{
+    return mode == LYAP_MODE_FAST ? fast() : (mode == LYAP_MODE_HOST ? host() : exact());
+}
+
+bool valid_mode(int mode) { return mode == LYAP_MODE_EXACT || mode == LYAP_MODE_FAST || mode == LYAP_MODE_HOST; }
+
+} // namespace
+
+extern "C" {
+
+const char *lyap_version(void) { return "lyapunov3d_b200 0.1 (sm_100a)"; }
+
+const char *lyap_error_string(int code)
+{
+    switch (code) {
+    case LYAP_OK: return "ok";
+    case LYAP_ERR_BAD_SEQUENCE: return "bad sequence (empty, symbol outside 0..3, or too long)";
+    case LYAP_ERR_BAD_ARGUMENT: return "bad argument";
+    case LYAP_ERR_NO_DEVICE: return "no CUDA device";
+    case LYAP_ERR_IO: return "i/o error";
+    default: return cudaGetErrorString((cudaError_t)code);
+    }
+}
+
+int lyap_set_option(const char *key, long value)
+{
+    if (!strcmp(key, "force_generic")) g_force_generic = value;
+    else if (!strcmp(key, "render_warps_per_sm")) g_render_warps_per_sm = value;
+    else if (!strcmp(key, "bake_blocks_per_sm")) g_bake_blocks_per_sm = value;
+    else return LYAP_ERR_BAD_ARGUMENT;
+    return LYAP_OK;
+}
+
+/* Which period instantiation a sequence would run on (0 = generic loop, -1 = invalid). */
+int lyap_plan_period(const int32_t *seq, uint32_t settle, uint32_t accum)
+{
+    SeqPlan sp;
+    return build_plan(sp, seq, settle, accum);
+}
+
+uint64_t lyap_tile_count(uint32_t width, uint32_t height, uint32_t tile, uint32_t rank, uint32_t world)
+{
+    if (!tile || !world || rank >= world) return 0;
+    const uint64_t tiles = (uint64_t)((width + tile - 1) / tile) * ((height + tile - 1) / tile);
+    const uint64_t mine = tiles / world + (rank < tiles % world ? 1 : 0);
+    return mine * tile * tile;
+}
+
+int lyap_render_tiles(lyap_rgba *d_rgba, lyap_point *d_points, const lyap_cam *cam, const lyap_params *prm,
+                      const int32_t *seq, const lyap_light *d_lights, uint32_t num_lights,
+                      uint32_t width, uint32_t height, uint32_t tile, uint32_t rank, uint32_t world,
+                      int compact, int mode, unsigned long long *d_evals, void *stream)
+{
+    if (!d_rgba || !d_points || !cam || !prm || !valid_mode(mode) || !width || !height || !tile || !world || rank >= world)
+        return LYAP_ERR_BAD_ARGUMENT;
+    if (num_lights > LYAP_MAX_LIGHTS || (num_lights && !d_lights)) return LYAP_ERR_BAD_ARGUMENT;
+    if ((uint64_t)width * height > 0xffffffffull) return LYAP_ERR_BAD_ARGUMENT;
+    RenderArgs a;
+    const int P = build_plan(a.plan, seq, prm->settle, prm->accum);
+    if (P < 0) return LYAP_ERR_BAD_SEQUENCE;
+    DeviceScratch *sc = nullptr;
+    cudaError_t e = scratch_for_current_device(&sc);
+    if (e != cudaSuccess) return (int)e;
+
+    a.cam = *cam;
+    a.prm = *prm;
+    a.rgba = d_rgba;
+    a.points = d_points;
+    a.lights = d_lights;
+    a.n_lights = num_lights;
+    a.width = width;
+    a.height = height;
+    a.tile = tile;
+    a.tiles_x = (width + tile - 1) / tile;
+    a.n_tiles = a.tiles_x * ((height + tile - 1) / tile);
+    a.rank = rank;
+    a.world = world;
+    a.compact = compact ? 1u : 0u;
+    a.n_items = lyap_tile_count(width, height, tile, rank, world);
+    a.evals = d_evals;
+    if (a.n_items == 0) return LYAP_OK;
+
+    cudaStream_t s = (cudaStream_t)stream;
+    a.queue = sc->counters + (sc->next.fetch_add(1) % kCounterRing);
+    if ((e = cudaMemsetAsync(a.queue, 0, sizeof(unsigned long long), s)) != cudaSuccess) return (int)e;
+
+    int per_sm = by_mode(mode, [&] { return render_blocks_per_sm_exact(P); }, [&] { return render_blocks_per_sm_fast(P); },
+                         [&] { return render_blocks_per_sm_host(P); });
+    if (per_sm <= 0) return (int)cudaErrorLaunchOutOfResources;
+    long want_warps = g_render_warps_per_sm.load();
+    if (want_warps <= 0) want_warps = kDefaultRenderWarpsPerSM;
+    int want_blocks = (int)((want_warps * 32 + kRenderThreads - 1) / kRenderThreads);
+    if (want_blocks < per_sm) per_sm = want_blocks;
+    unsigned long long grid = (unsigned long long)sc->sm_count * per_sm;
+    const unsigned long long max_useful = (a.n_items + kRenderThreads - 1) / kRenderThreads;
+    if (grid > max_useful) grid = max_useful;
+
+    e = by_mode(mode, [&] { return launch_render_exact(P, a, (unsigned)grid, s); },
+                [&] { return launch_render_fast(P, a, (unsigned)grid, s); },
+                [&] { return launch_render_host(P, a, (unsigned)grid, s); });
+    return (int)e;
+}
+
+int lyap_render(lyap_rgba *d_rgba, lyap_point *d_points, const lyap_cam *cam, const lyap_params *prm,
+                const int32_t *seq, const lyap_light *d_lights, uint32_t num_lights,
+                uint32_t width, uint32_t height, int mode, unsigned long long *d_evals, void *stream)
+{
+    return lyap_render_tiles(d_rgba, d_points, cam, prm, seq, d_lights, num_lights, width, height, 8, 0, 1, 0, mode, d_evals, stream);
+}
+
+int lyap_scatter_tiles(void *d_image, const void *d_compact, uint32_t elem_size, uint32_t width, uint32_t height,
+                       uint32_t tile, uint32_t rank, uint32_t world, void *stream)
+{
+    if (!d_image || !d_compact || !elem_size || !tile || !world || rank >= world) return LYAP_ERR_BAD_ARGUMENT;
+    ScatterArgs a;
+    a.image = (uint8_t *)d_image;
+    a.compact = (const uint8_t *)d_compact;
+    a.elem = elem_size;
+    a.width = width;
+    a.height = height;
+    a.tile = tile;
+    a.tiles_x = (width + tile - 1) / tile;
+    a.n_tiles = a.tiles_x * ((height + tile - 1) / tile);
+    a.rank = rank;
+    a.world = world;
+    a.n_items = lyap_tile_count(width, height, tile, rank, world);
+    if (!a.n_items) return LYAP_OK;
+    const unsigned grid = (unsigned)((a.n_items + 255) / 256 < 4096 ? (a.n_items + 255) / 256 : 4096);
+    return (int)launch_scatter(a, grid, (cudaStream_t)stream);
+}
+
+int lyap_shade_points(lyap_rgba *d_rgba, const lyap_point *d_points, const lyap_cam *cam,
+                      const lyap_light *d_lights, uint32_t num_lights, uint64_t count, int mode, void *stream)
+{
+    if (!d_rgba || !d_points || !cam || !valid_mode(mode) || num_lights > LYAP_MAX_LIGHTS) return LYAP_ERR_BAD_ARGUMENT;
+    if (!count) return LYAP_OK;
+    ShadeArgs a;
+    a.cam = *cam;
+    a.rgba = d_rgba;
+    a.points = d_points;
+    a.lights = d_lights;
+    a.n_lights = num_lights;
+    a.count = count;
+    const unsigned grid = (unsigned)((count + 255) / 256 < 8192 ? (count + 255) / 256 : 8192);
+    return (int)launch_shade(mode, a, grid, (cudaStream_t)stream);
+}
+
+int lyap_bake(void *d_exps, int dtype, const lyap_params *prm, const int32_t *seq,
+              uint32_t nx, uint32_t ny, uint32_t nz, uint32_t z0, uint32_t z1, int mode, void *stream)
+{
+    if (!d_exps || !prm || !valid_mode(mode) || !nx || !ny || !nz || z1 > nz || z0 > z1) return LYAP_ERR_BAD_ARGUMENT;
+    if (dtype != LYAP_F32 && dtype != LYAP_F16) return LYAP_ERR_BAD_ARGUMENT;
+    BakeArgs a;
+    const int P = build_plan(a.plan, seq, prm->settle, prm->accum);
+    if (P < 0) return LYAP_ERR_BAD_SEQUENCE;
+    if (z0 == z1) return LYAP_OK;
+    DeviceScratch *sc = nullptr;
+    cudaError_t e = scratch_for_current_device(&sc);
+    if (e != cudaSuccess) return (int)e;
+    a.d = prm->d;
+    a.out = d_exps;
+    a.f16 = dtype == LYAP_F16;
+    a.nx = nx; a.ny = ny; a.nz = nz; a.z0 = z0; a.z1 = z1;
+
+    int per_sm = by_mode(mode, [&] { return bake_blocks_per_sm_exact(P); }, [&] { return bake_blocks_per_sm_fast(P); },
+                         [&] { return bake_blocks_per_sm_host(P); });
+    if (per_sm <= 0) return (int)cudaErrorLaunchOutOfResources;
+    const long cap = g_bake_blocks_per_sm.load();
+    if (cap > 0 && cap < per_sm) per_sm = (int)cap;
+    const unsigned long long total = (unsigned long long)nx * ny * (z1 - z0);
+    unsigned long long grid = (unsigned long long)sc->sm_count * per_sm;
+    if (grid > (total + 255) / 256) grid = (total + 255) / 256;
+    cudaStream_t s = (cudaStream_t)stream;
+    e = by_mode(mode, [&] { return launch_bake_exact(P, a, (unsigned)grid, s); }, [&] { return launch_bake_fast(P, a, (unsigned)grid, s); },
+                [&] { return launch_bake_host(P, a, (unsigned)grid, s); });
+    return (int)e;
+}
+
+int lyap_exponent_points(float *d_out, const float *d_xyz, uint64_t n, const lyap_params *prm,
+                         const int32_t *seq, int mode, void *stream)
+{
+    if (!d_out || !d_xyz || !prm || !valid_mode(mode)) return LYAP_ERR_BAD_ARGUMENT;
+    PointsArgs a;
+    const int P = build_plan(a.plan, seq, prm->settle, prm->accum);
+    if (P < 0) return LYAP_ERR_BAD_SEQUENCE;
+    if (!n) return LYAP_OK;
+    DeviceScratch *sc = nullptr;
+    cudaError_t e = scratch_for_current_device(&sc);
+    if (e != cudaSuccess) return (int)e;
+    a.d = prm->d;
+    a.xyz = d_xyz;
+    a.out = d_out;
+    a.n = n;
+    unsigned long long grid = (unsigned long long)sc->sm_count * 4;
+    if (grid > (n + 255) / 256) grid = (n + 255) / 256;
+    cudaStream_t s = (cudaStream_t)stream;
+    e = by_mode(mode, [&] { return launch_points_exact(P, a, (unsigned)grid, s); }, [&] { return launch_points_fast(P, a, (unsigned)grid, s); },
+                [&] { return launch_points_host(P, a, (unsigned)grid, s); });
+    return (int)e;
+}
+
+// --------------------------------------------------------------- host-buffer path
+int lyap_render_host(lyap_rgba *h_rgba, lyap_point *h_points, const lyap_cam *cam, const lyap_params *prm,
+                     const int32_t *seq, const lyap_light *h_lights, uint32_t num_lights,
+                     uint32_t width, uint32_t height, int mode, int device, unsigned long long *evals_out)
+{
+    if (!h_rgba || !cam || !prm || (num_lights && !h_lights)) return LYAP_ERR_BAD_ARGUMENT;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return (int)e;
+    const size_t n = (size_t)width * height;
+    lyap_rgba *d_rgba = nullptr;
+    lyap_point *d_points = nullptr;
+    lyap_light *d_lights = nullptr;
+    unsigned long long *d_evals = nullptr;
+    int rc = LYAP_OK;
+    cudaStream_t s = nullptr;
+    do {
+        if ((e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)) != cudaSuccess) break;
+        if ((e = cudaMalloc(&d_rgba, n * sizeof(lyap_rgba))) != cudaSuccess) break;
+        if ((e = cudaMalloc(&d_points, n * sizeof(lyap_point))) != cudaSuccess) break;
+        if ((e = cudaMalloc(&d_lights, sizeof(lyap_light) * LYAP_MAX_LIGHTS)) != cudaSuccess) break;
+        if ((e = cudaMalloc(&d_evals, sizeof(unsigned long long))) != cudaSuccess) break;
+        // the reference never clears its point buffer; zero gives miss pixels a defined colour
+        if ((e = cudaMemsetAsync(d_points, 0, n * sizeof(lyap_point), s)) != cudaSuccess) break;
+        if ((e = cudaMemsetAsync(d_rgba, 0, n * sizeof(lyap_rgba), s)) != cudaSuccess) break;
+        if ((e = cudaMemsetAsync(d_evals, 0, sizeof(unsigned long long), s)) != cudaSuccess) break;
+        if (num_lights && (e = cudaMemcpyAsync(d_lights, h_lights, sizeof(lyap_light) * num_lights, cudaMemcpyHostToDevice, s)) != cudaSuccess) break;
+        rc = lyap_render(d_rgba, d_points, cam, prm, seq, d_lights, num_lights, width, height, mode, d_evals, s);
+        if (rc != LYAP_OK) break;
+        if ((e = cudaMemcpyAsync(h_rgba, d_rgba, n * sizeof(lyap_rgba), cudaMemcpyDeviceToHost, s)) != cudaSuccess) break;
+        if (h_points && (e = cudaMemcpyAsync(h_points, d_points, n * sizeof(lyap_point), cudaMemcpyDeviceToHost, s)) != cudaSuccess) break;
+        unsigned long long ev = 0;
+        if ((e = cudaMemcpyAsync(&ev, d_evals, sizeof ev, cudaMemcpyDeviceToHost, s)) != cudaSuccess) break;
+        if ((e = cudaStreamSynchronize(s)) != cudaSuccess) break;
+        if (evals_out) *evals_out = ev;
+    } while (0);
+    cudaFree(d_rgba);
+    cudaFree(d_points);
+    cudaFree(d_lights);
+    cudaFree(d_evals);
+    if (s) cudaStreamDestroy(s);
+    if (rc != LYAP_OK) return rc;
+    return (int)e;
+}
+
+int lyap_bake_host(void *h_exps, int dtype, const lyap_params *prm, const int32_t *seq,
+                   uint32_t nx, uint32_t ny, uint32_t nz, uint32_t z0, uint32_t z1, int mode, int device)
+{
+    if (!h_exps || !prm || z1 > nz || z0 > z1) return LYAP_ERR_BAD_ARGUMENT;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return (int)e;
+    const size_t esz = dtype == LYAP_F16 ? 2 : 4;
+    const size_t plane = (size_t)nx * ny;
+    const size_t bytes = plane * (z1 - z0) * esz;
+    if (!bytes) return LYAP_OK;
+    // the slab is contiguous in the volume: allocate just the slab and bias the base pointer
+    char *d_slab = nullptr;
+    cudaStream_t s = nullptr;
+    int rc = LYAP_OK;
+    do {
+        if ((e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)) != cudaSuccess) break;
+        if ((e = cudaMalloc(&d_slab, bytes)) != cudaSuccess) break;
+        rc = lyap_bake(d_slab - plane * z0 * esz, dtype, prm, seq, nx, ny, nz, z0, z1, mode, s);
+        if (rc != LYAP_OK) break;
+        if ((e = cudaMemcpyAsync((char *)h_exps + plane * z0 * esz, d_slab, bytes, cudaMemcpyDeviceToHost, s)) != cudaSuccess) break;
+        e = cudaStreamSynchronize(s);
+    } while (0);
+    cudaFree(d_slab);
+    if (s) cudaStreamDestroy(s);
+    if (rc != LYAP_OK) return rc;
+    return (int)e;
+}
+
+int lyap_probe_peaks(double *ffma_lane_ops_per_s, double *mufu_lane_ops_per_s, double *sm_clock_hz_est, int *sm_count)
+{
+    double f = 0, m = 0, c = 0;
+    int n = 0;
+    const cudaError_t e = probe_peaks(&f, &m, &c, &n);
+    if (e != cudaSuccess) return (int)e;
+    if (ffma_lane_ops_per_s) *ffma_lane_ops_per_s = f;
+    if (mufu_lane_ops_per_s) *mufu_lane_ops_per_s = m;
+    if (sm_clock_hz_est) *sm_clock_hz_est = c;
+    if (sm_count) *sm_count = n;
+    return LYAP_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,232 @@
+// exponent.cuh -- the per-sample Lyapunov exponent (reference kernel.cu:108-154, lyap4d).
+//
+// One call = settle + accum steps of the sequence-forced logistic map for ONE
+// sample point per lane.  The trip count is uniform across a warp, so every lane
+// of a warp stays busy for the whole call; all divergence lives in the callers.
+//
+// Trajectory.  The reference evaluates v <- r*v*(1.0 - v) with a float product
+// r*v and a double tail.  p = r*v; v' = fma(-p, v, p) gives the same float, bit
+// for bit, as does fma(-2r, v', r) for the derivative
+// r - 2.0*r*v'.  Two FP32 instructions per step, no FP64, no conversions.
+//
+// Three accumulators share that trajectory:
+//   kExact  l = fma(lg2.approx(|d|), ln2, l) every step -- the exact PTX ops of the
+//           reference's fast-math build, so l is bit-identical to the reference
+//           kernel on the same GPU.  4 FP32 + 1 MUFU per step: SFU-bound.
+//   kFast   the derivative's magnitude is multiplied up instead:
+//           prod *= |1 - 2v'|, exponent folded out with integer ops every <= 10
+//           steps, one lg2 at the end; sum(log r) is added analytically from the
+//           per-symbol counts.  4 FP32 per step, no MUFU in the loop: FP32-bound.
+//   kHost   IEEE adds of a glibc-exact logf per step (reference host build).
+//
+// Sequence.  The symbol sequence is warp-uniform.  For a period P <= 32 the
+// per-position multipliers live in P registers and the period is fully
+// unrolled (template parameter P); anything else takes the generic loop that
+// selects the multiplier per step (P == 0).
+#pragma once
+#include "arith.cuh"
+#include "hostlog.cuh"
+
+namespace lyap {
+
+constexpr int kMaxSeq = 1024;       // symbols per period accepted by the ABI
+constexpr int kMaxPeriodRegs = 32;  // longest period served by the register-table path
+
+enum Mode { kExact = 0, kFast = 1, kHost = 2 };
+
+// Uniform description of the iteration schedule; lives in kernel parameter space.
+struct SeqPlan {
+    uint32_t len;             // period in symbols
+    uint32_t settle, accum;   // reference prm.settle / prm.accum
+    uint32_t settle_head;     // settle % len: steps taken before the rotated periods start
+    uint32_t settle_periods;  // settle / len
+    uint32_t accum_periods;   // accum / len
+    uint32_t accum_tail;      // accum % len
+    uint32_t cnt[4];          // how often each symbol occurs among the accum steps
+    uint8_t rot[kMaxPeriodRegs];  // sym rotated left by settle_head: the order both period loops see
+    uint8_t sym[kMaxSeq];         // the period as written
+};
+
+__device__ __forceinline__ float sel4(uint32_t s, float x, float y, float z, float d)
+{
+    return s == 0 ? x : (s == 1 ? y : (s == 2 ? z : d));
+}
+
+// ---------------------------------------------------------------- trajectory
+template <int MODE>
+__device__ __forceinline__ void logistic_step(float r, float &v)
+{
+    if constexpr (MODE == kExact) {
+        float p = ArithDev::mul(r, v);
+        v = ArithDev::fma(-p, v, p);
+    } else {
+        float p = __fmul_rn(r, v);
+        v = __fmaf_rn(-p, v, p);
+    }
+}
+
+// --------------------------------------------------------------- accumulators
+template <int MODE>
+struct Accum;
+
+template <>
+struct Accum<kExact> {
+    float l;
+    __device__ __forceinline__ void init() { l = 0.0f; }
+    __device__ __forceinline__ void step(float r, float &v)
+    {
+        logistic_step<kExact>(r, v);
+        float d = ArithDev::fma(-(r + r), v, r);
+        l = ArithDev::fma(ArithDev::lg2(fabsf(d)), 0.693147182f, l);
+    }
+    __device__ __forceinline__ void renorm() {}
+    // +-inf and NaN are absorbing under the adds above, so the reference's per-step
+    // isfinite() early-out (kernel.cu:147) equals one test here.
+    __device__ __forceinline__ float finish(const SeqPlan &sp, float, float, float, float, float)
+    {
+        return is_finite(l) ? ArithDev::div(l, __uint2float_rn(sp.accum)) : quiet_nan();
+    }
+};
+
+template <>
+struct Accum<kHost> {
+    float l;
+    __device__ __forceinline__ void init() { l = 0.0f; }
+    __device__ __forceinline__ void step(float r, float &v)
+    {
+        logistic_step<kHost>(r, v);
+        float d = __fmaf_rn(-(r + r), v, r);
+        l = __fadd_rn(l, glibc_logf(fabsf(d)));
+    }
+    __device__ __forceinline__ void renorm() {}
+    __device__ __forceinline__ float finish(const SeqPlan &sp, float, float, float, float, float)
+    {
+        return is_finite(l) ? __fdiv_rn(l, __uint2float_rn(sp.accum)) : quiet_nan();
+    }
+};
+
+template <>
+struct Accum<kFast> {
+    // prod is kept in [2^kBias, 2^(kBias+1)) after each fold.  |1-2v| is 0 or at
+    // least 2^-24 for any float v in [0,1], and never above 1, so ten steps can
+    // take prod no lower than 2^(kBias-240) > 2^-126: no underflow is possible and
+    // a zero exponent field can only mean a true zero derivative.
+    static constexpr int kBias = 120;
+    static constexpr int kFoldEvery = 10;
+    float prod;
+    int esum, emin;
+    __device__ __forceinline__ void init()
+    {
+        prod = __int_as_float((127 + kBias) << 23);
+        esum = 0;
+        emin = 255;
+    }
+    __device__ __forceinline__ void step(float r, float &v)
+    {
+        logistic_step<kFast>(r, v);
+        float q = __fmaf_rn(-2.0f, v, 1.0f);
+        prod = __fmul_rn(prod, fabsf(q));
+    }
+    __device__ __forceinline__ void renorm()
+    {
+        int bits = __float_as_int(prod);
+        int e = bits >> 23;  // prod >= 0: no sign bit
+        esum += e - (127 + kBias);
+        emin = min(emin, e);
+        prod = __int_as_float((bits & 0x007fffff) | ((127 + kBias) << 23));
+    }
+    __device__ __forceinline__ float finish(const SeqPlan &sp, float x, float y, float z, float d, float v)
+    {
+        renorm();
+        float mant = __int_as_float((__float_as_int(prod) & 0x007fffff) | 0x3f800000);
+        double l2 = (double)esum + (double)__log2f(mant);
+        if (sp.cnt[0]) l2 += (double)sp.cnt[0] * (double)__log2f(fabsf(x));
+        if (sp.cnt[1]) l2 += (double)sp.cnt[1] * (double)__log2f(fabsf(y));
+        if (sp.cnt[2]) l2 += (double)sp.cnt[2] * (double)__log2f(fabsf(z));
+        if (sp.cnt[3]) l2 += (double)sp.cnt[3] * (double)__log2f(fabsf(d));
+        float l = (float)(l2 * (0.6931471805599453 / (double)sp.accum));
+        // zero derivative somewhere (log -> -inf) or an orbit that left [0,1] for good
+        bool bad = (emin == 0) || !is_finite(v) || !is_finite(l);
+        return bad ? quiet_nan() : l;
+    }
+};
+
+// -------------------------------------------------------------------- driver
+template <int P>
+struct PeriodUnroll {
+    static constexpr int U = (P >= 11) ? 1 : (20 / (P > 0 ? P : 1));  // periods per loop body
+};
+
+template <int MODE, int P>
+__device__ __forceinline__ float exponent(const SeqPlan &sp, float x, float y, float z, float d)
+{
+    float v = 0.5f;
+    Accum<MODE> acc;
+    acc.init();
+    float v_settled;
+
+    if constexpr (P > 0) {
+        float r[P];
+#pragma unroll
+        for (int k = 0; k < P; k++) r[k] = sel4(sp.rot[k], x, y, z, d);
+
+        // settle: a partial period in written order, then whole periods in rotated order
+        for (uint32_t n = 0; n < sp.settle_head; n++) logistic_step<MODE>(sel4(sp.sym[n], x, y, z, d), v);
+#pragma unroll 1
+        for (uint32_t i = 0; i < sp.settle_periods; i++) {
+#pragma unroll
+            for (int k = 0; k < P; k++) logistic_step<MODE>(r[k], v);
+        }
+        v_settled = v;
+
+        // accumulate: whole periods (rotated order continues seamlessly), then a partial one
+        constexpr int U = PeriodUnroll<P>::U;
+        const uint32_t groups = sp.accum_periods / U;
+#pragma unroll 1
+        for (uint32_t g = 0; g < groups; g++) {
+#pragma unroll
+            for (int s = 0; s < U * P; s++) {
+                acc.step(r[s % P], v);
+                if ((s + 1) % Accum<kFast>::kFoldEvery == 0 || s + 1 == U * P) acc.renorm();
+            }
+        }
+        if constexpr (U > 1) {
+#pragma unroll 1
+            for (uint32_t i = groups * U; i < sp.accum_periods; i++) {
+#pragma unroll
+                for (int k = 0; k < P; k++) acc.step(r[k], v);
+                acc.renorm();
+            }
+        }
+#pragma unroll 1
+        for (uint32_t n = 0; n < sp.accum_tail; n++) {
+            acc.step(sel4(sp.rot[n], x, y, z, d), v);
+            if ((n & 7) == 7) acc.renorm();
+        }
+    } else {
+        uint32_t pos = 0;
+#pragma unroll 1
+        for (uint32_t n = 0; n < sp.settle; n++) {
+            logistic_step<MODE>(sel4(sp.sym[pos], x, y, z, d), v);
+            pos = (pos + 1 == sp.len) ? 0 : pos + 1;
+        }
+        v_settled = v;
+#pragma unroll 1
+        for (uint32_t n = 0; n < sp.accum; n++) {
+            acc.step(sel4(sp.sym[pos], x, y, z, d), v);
+            pos = (pos + 1 == sp.len) ? 0 : pos + 1;
+            if ((n & 7) == 7) acc.renorm();
+        }
+    }
+
+    float l = acc.finish(sp, x, y, z, d, v);
+    // reference kernel.cu:138: an orbit sitting on v == 0.5 after settling skips the
+    // accumulation and reports l = 0 / accum
+    if (v_settled == 0.5f) {
+        if constexpr (MODE == kExact) l = ArithDev::div(0.0f, __uint2float_rn(sp.accum));
+        else l = __fdiv_rn(0.0f, __uint2float_rn(sp.accum));
+    }
+    return l;
+}
+
+} // namespace lyap

@@ -1,0 +1,80 @@
+// hostlog.cuh -- glibc 2.39 logf(), bit for bit, on the device.
+//
+// LYAP_MODE_HOST has to reproduce the exponent of the reference's HOST build,
+// whose `l += logf(r)` calls glibc.  The algorithm lives in a third-party
+// dependency that is not vendored by the reference: GNU libc 2.39
+// (Ubuntu 2.39-0ubuntu8.5 in this image), sysdeps/ieee754/flt-32/e_logf.c with the
+// table of e_logf_data.c (Szabolcs Nagy's "optimized routines" logf):
+//
+//   x = 2^k * z, z in [0x1.66p-1, 0x1.66p0) picked by subtracting OFF = 0x3f330000
+//   from the bits; i = top 4 mantissa bits of the shifted value;
+//   r = z*invc[i] - 1;  y0 = logc[i] + k*ln2;
+//   y = (A0*r^2 + (A1*r + A2)) * r^2 + (y0 + r);  return (float)y   (all in double)
+//
+// The 16-entry (invc, logc) table, ln2 and A[] below were read out of this image's
+// libm.so.6 (.rodata, located by the ln2 bit pattern) and agree with the upstream
+// source.  With or without FMA contraction of the double expressions the float
+// result is the same except when y lies within ~1e-16 of a rounding boundary:
+// 0 differences against the installed libm over 3e8 inputs for both forms, so the
+// fused form (7 FP64 ops) is used here.
+//
+// int->double and float->double conversions are done with integer bit
+// construction instead of F2F/I2F (XU pipe); only the final double->float
+// rounding uses a conversion instruction.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lyap {
+
+static __device__ const double kLogfTab[32] = {
+    0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2, 0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2,
+    0x1.49539f0f010b0p+0, -0x1.01eae7f513a67p-2, 0x1.3c995b0b80385p+0, -0x1.b31d8a68224e9p-3,
+    0x1.30d190c8864a5p+0, -0x1.6574f0ac07758p-3, 0x1.25e227b0b8ea0p+0, -0x1.1aa2bc79c8100p-3,
+    0x1.1bb4a4a1a343fp+0, -0x1.a4e76ce8c0e5ep-4, 0x1.12358f08ae5bap+0, -0x1.1973c5a611cccp-4,
+    0x1.0953f419900a7p+0, -0x1.252f438e10c1ep-5, 0x1p+0,               0x0p+0,
+    0x1.e608cfd9a47acp-1, 0x1.aa5aa5df25984p-5,  0x1.ca4b31f026aa0p-1, 0x1.c5e53aa362eb4p-4,
+    0x1.b2036576afce6p-1, 0x1.526e57720db08p-3,  0x1.9c2d163a1aa2dp-1, 0x1.bc2860d224770p-3,
+    0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2,  0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2};
+
+// Per-block copy of the table: the index differs per lane, which shared memory
+// serves at full rate and the constant cache would serialise.
+static __shared__ double2 s_logf_tab[16];
+
+__device__ __forceinline__ void hostlog_init()
+{
+    if (threadIdx.x < 16) s_logf_tab[threadIdx.x] = make_double2(kLogfTab[2 * threadIdx.x], kLogfTab[2 * threadIdx.x + 1]);
+    __syncthreads();
+}
+
+// x must be >= +0 or NaN (callers pass |d|).
+__device__ __forceinline__ float glibc_logf(float x)
+{
+    uint32_t ix = __float_as_uint(x);
+    if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {
+        // zero, subnormal, inf or nan
+        if (ix * 2 == 0) return __int_as_float(0xff800000);          // log(0) = -inf
+        if (ix == 0x7f800000u) return x;                              // log(inf) = inf
+        if ((ix & 0x80000000u) || ix * 2 >= 0xff000000u) return __int_as_float(0x7fc00000);
+        ix = __float_as_uint(__fmul_rn(x, 8388608.0f));               // subnormal: scale by 2^23 (exact)
+        ix -= 23u << 23;
+    }
+    const uint32_t tmp = ix - 0x3f330000u;
+    const int i = (tmp >> 19) & 15;
+    const int k = (int)tmp >> 23;
+    const uint32_t iz = ix - (tmp & 0xff800000u);
+    const double2 t = s_logf_tab[i];
+    // z = (double)asfloat(iz): iz is a normal float in [0.699, 1.399)
+    const double z = __hiloint2double((int)((iz >> 3) + 0x38000000u), (int)(iz << 29));
+    // (double)k without I2F: 2^52 + 2^31 + k is exact in the low word
+    const double kd = __hiloint2double(0x43300000, (int)((uint32_t)k ^ 0x80000000u)) - 4503601774854144.0;
+    const double r = __fma_rn(z, t.x, -1.0);
+    const double y0 = __fma_rn(kd, 0x1.62e42fefa39efp-1, t.y);
+    const double r2 = __dmul_rn(r, r);
+    double y = __fma_rn(0x1.5575b0be00b6ap-2, r, -0x1.ffffef20a4123p-2);
+    y = __fma_rn(-0x1.00ea348b88334p-2, r2, y);
+    y = __fma_rn(y, r2, __dadd_rn(y0, r));
+    return __double2float_rn(y);
+}
+
+} // namespace lyap

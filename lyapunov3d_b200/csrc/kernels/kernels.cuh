@@ -1,0 +1,214 @@
+// kernels.cuh -- the __global__ kernels (templated on exponent mode and sequence
+// period) and the argument blocks they take by value.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "exponent.cuh"
+#include "ray.cuh"
+
+namespace lyap {
+
+template <int MODE>
+struct ArithOf { using type = ArithDev; };
+template <>
+struct ArithOf<kHost> { using type = ArithHost; };
+
+// ----------------------------------------------------------------- volume bake
+// Replaces kernel_calc_volume (reference kernel.cu:518-532).  The reference maps an
+// 8x8x8 thread cube to voxels, so a warp stores four 32-byte fragments; here
+// consecutive lanes own consecutive x, every warp store is one full 128-byte line
+// (64 bytes for FP16), and a persistent grid strides over the slab.
+struct BakeArgs {
+    SeqPlan plan;
+    float d;
+    void *out;       // full volume
+    int f16;         // 0: float, 1: __half
+    uint32_t nx, ny, nz, z0, z1;
+};
+
+template <int MODE>
+__device__ __forceinline__ float voxel_coord(uint32_t i, uint32_t n)
+{
+    // a = 4.0f * (float)x / (float)N  (kernel.cu:527-529); device build: mul.ftz then div.approx
+    if constexpr (MODE == kHost) return __fdiv_rn(__fmul_rn(4.0f, __uint2float_rn(i)), __uint2float_rn(n));
+    else return ArithDev::div(ArithDev::mul(__uint2float_rn(i), 4.0f), __uint2float_rn(n));
+}
+
+template <int MODE, int P>
+__global__ void __launch_bounds__(256) bake_kernel(const __grid_constant__ BakeArgs a)
+{
+    if constexpr (MODE == kHost) hostlog_init();
+    const uint64_t plane = (uint64_t)a.nx * a.ny;
+    const uint64_t total = plane * (a.z1 - a.z0);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const uint32_t z = a.z0 + (uint32_t)(i / plane);
+        const uint32_t rem = (uint32_t)(i % plane);
+        const uint32_t y = rem / a.nx, x = rem % a.nx;
+        const float l = exponent<MODE, P>(a.plan, voxel_coord<MODE>(x, a.nx), voxel_coord<MODE>(y, a.ny),
+                                          voxel_coord<MODE>(z, a.nz), a.d);
+        const uint64_t idx = (uint64_t)z * plane + rem;
+        if (a.f16) reinterpret_cast<__half *>(a.out)[idx] = __float2half_rn(l);
+        else reinterpret_cast<float *>(a.out)[idx] = l;
+    }
+}
+
+// ------------------------------------------------------- exponent at given points
+struct PointsArgs {
+    SeqPlan plan;
+    float d;
+    const float *xyz;
+    float *out;
+    uint64_t n;
+};
+
+template <int MODE, int P>
+__global__ void __launch_bounds__(256) points_kernel(const __grid_constant__ PointsArgs a)
+{
+    if constexpr (MODE == kHost) hostlog_init();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride)
+        a.out[i] = exponent<MODE, P>(a.plan, a.xyz[3 * i], a.xyz[3 * i + 1], a.xyz[3 * i + 2], a.d);
+}
+
+// ---------------------------------------------------------------------- render
+// Replaces kernel_calc_render (reference kernel.cu:500-516): persistent warps pull
+// pixels from a global queue; each lane carries one ray (ray.cuh) and the warp
+// alternates between ONE uniform exponent evaluation for all 32 lanes and a short
+// divergent state update.  Lanes whose ray finished are refilled with a single
+// warp-aggregated atomic (ballot / popc / shfl).
+struct RenderArgs {
+    SeqPlan plan;
+    lyap_cam cam;
+    lyap_params prm;
+    lyap_rgba *rgba;
+    lyap_point *points;
+    const lyap_light *lights;
+    uint32_t n_lights;
+    uint32_t width, height;
+    uint32_t tile, tiles_x, n_tiles;   // tile edge, tiles per row, tiles in the image
+    uint32_t rank, world;              // this launch renders tiles j with j % world == rank
+    uint32_t compact;                  // write outputs densely in work order
+    unsigned long long n_items;        // work items of this rank: its tiles * tile^2
+    unsigned long long *queue;         // next work item (zeroed before launch)
+    unsigned long long *evals;         // optional: += exponent evaluations
+};
+
+constexpr int kRenderThreads = 128;
+
+// Work item k of a rank -> pixel.  Returns false for the padding of ragged edge tiles.
+__device__ __forceinline__ bool item_to_pixel(const RenderArgs &a, unsigned long long k, uint32_t &x, uint32_t &y)
+{
+    const uint32_t tt = a.tile * a.tile;
+    const uint32_t m = (uint32_t)(k / tt), p = (uint32_t)(k % tt);
+    const uint32_t j = m * a.world + a.rank;
+    x = (j % a.tiles_x) * a.tile + p % a.tile;
+    y = (j / a.tiles_x) * a.tile + p / a.tile;
+    return j < a.n_tiles && x < a.width && y < a.height;
+}
+
+template <class A>
+__device__ __forceinline__ void finish_pixel(const RenderArgs &a, const RayState &st, bool hit)
+{
+    lyap_point pt;
+    if (hit) {
+        pt.P.x = st.Px; pt.P.y = st.Py; pt.P.z = st.Pz;
+        pt.N.x = st.Nx; pt.N.y = st.Ny; pt.N.z = st.Nz;
+        pt.a = st.a; pt.c = st.c; pt.l = st.l;
+        a.points[st.out] = pt;
+    } else {
+        pt = a.points[st.out];   // a miss shades whatever the caller left there (kernel.cu:508-512)
+    }
+    reinterpret_cast<uint32_t *>(a.rgba)[st.out] = shade_pixel<A>(pt, a.cam, a.lights, a.n_lights);
+}
+
+template <int MODE, int P>
+__global__ void __launch_bounds__(kRenderThreads) render_kernel(const __grid_constant__ RenderArgs a)
+{
+    using A = typename ArithOf<MODE>::type;
+    if constexpr (MODE == kHost) hostlog_init();
+
+    const unsigned full = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31;
+    RayState st;
+    st.phase = kNeedRay;
+    st.sx = st.sy = st.sz = 2.0f;
+    bool drained = false;
+    unsigned long long evals = 0;
+
+    for (;;) {
+        // ---- refill idle lanes from the queue
+        for (;;) {
+            const bool need = st.phase == kNeedRay;
+            const unsigned m = __ballot_sync(full, need);
+            if (m == 0 || drained) break;
+            const int leader = __ffs(m) - 1;
+            const unsigned n_need = __popc(m);
+            unsigned long long base = 0;
+            if ((int)lane == leader) base = atomicAdd(a.queue, (unsigned long long)n_need);
+            base = __shfl_sync(full, base, leader);
+            if (need) {
+                const unsigned long long k = base + __popc(m & ((1u << lane) - 1u));
+                uint32_t px, py;
+                if (k < a.n_items && item_to_pixel(a, k, px, py)) {
+                    st.out = a.compact ? (uint32_t)k : px + py * a.width;
+                    if (!ray_begin<A>(st, px, py, a.cam, a.prm)) finish_pixel<A>(a, st, false);
+                }
+            }
+            if (base + n_need >= a.n_items) drained = true;
+        }
+        const bool active = st.phase != kNeedRay;
+        if (__ballot_sync(full, active) == 0) break;
+
+        // ---- one exponent for every lane (idle lanes evaluate a dummy point)
+        const float l = exponent<MODE, P>(a.plan, st.sx, st.sy, st.sz, a.prm.d);
+
+        // ---- advance each ray by that one sample
+        if (active) {
+            ++evals;
+            const RayEvent ev = ray_advance<A>(st, l, a.prm);
+            if (ev != kContinue) {
+                finish_pixel<A>(a, st, ev == kHit);
+                st.phase = kNeedRay;
+            }
+        }
+    }
+
+    if (a.evals) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) evals += __shfl_xor_sync(full, evals, o);
+        if (lane == 0) atomicAdd(a.evals, evals);
+    }
+}
+
+// Shade-only pass over stored points (no marching): one thread per point.
+struct ShadeArgs {
+    lyap_cam cam;
+    lyap_rgba *rgba;
+    const lyap_point *points;
+    const lyap_light *lights;
+    uint32_t n_lights;
+    unsigned long long count;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256) shade_kernel(const __grid_constant__ ShadeArgs a)
+{
+    using A = typename ArithOf<MODE>::type;
+    if constexpr (MODE == kHost) hostlog_init();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.count; i += stride)
+        reinterpret_cast<uint32_t *>(a.rgba)[i] = shade_pixel<A>(a.points[i], a.cam, a.lights, a.n_lights);
+}
+
+// Place one rank's compact (work-order) buffer into the full image.
+struct ScatterArgs {
+    uint8_t *image;
+    const uint8_t *compact;
+    uint32_t elem, width, height, tile, tiles_x, n_tiles, rank, world;
+    unsigned long long n_items;
+};
+
+__global__ void __launch_bounds__(256) scatter_kernel(const __grid_constant__ ScatterArgs a);
+
+} // namespace lyap

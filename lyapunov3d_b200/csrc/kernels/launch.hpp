@@ -1,0 +1,32 @@
+// launch.hpp -- host-visible launchers; one set per exponent mode, each compiled in
+// its own translation unit (tu_*.cu) so the period instantiations build in parallel.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "kernels.cuh"
+
+// Sequence periods with a register-table instantiation.  A period p runs on the
+// smallest listed multiple of p (the host replicates the sequence); anything else
+// uses the generic per-step-select loop (0).
+#define LYAP_PERIODS(X) \
+    X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) \
+    X(18) X(20) X(21) X(22) X(24) X(26) X(27) X(28) X(30) X(32)
+
+namespace lyap {
+
+#define LYAP_DECLARE_MODE(NAME)                                                                          \
+    cudaError_t launch_bake_##NAME(int P, const BakeArgs &a, unsigned grid, cudaStream_t s);              \
+    cudaError_t launch_points_##NAME(int P, const PointsArgs &a, unsigned grid, cudaStream_t s);          \
+    cudaError_t launch_render_##NAME(int P, const RenderArgs &a, unsigned grid, cudaStream_t s);          \
+    int render_blocks_per_sm_##NAME(int P);                                                               \
+    int bake_blocks_per_sm_##NAME(int P);
+
+LYAP_DECLARE_MODE(exact)
+LYAP_DECLARE_MODE(fast)
+LYAP_DECLARE_MODE(host)
+
+cudaError_t launch_shade(int mode, const ShadeArgs &a, unsigned grid, cudaStream_t s);
+cudaError_t launch_scatter(const ScatterArgs &a, unsigned grid, cudaStream_t s);
+cudaError_t probe_peaks(double *ffma_ops, double *mufu_ops, double *clock_hz, int *sms);
+
+} // namespace lyap

@@ -1,0 +1,135 @@
+// misc.cu -- shade-only pass, tile scatter, and the roofline probe kernels.
+#include <cstdio>
+
+#include "launch.hpp"
+
+namespace lyap {
+
+cudaError_t launch_shade(int mode, const ShadeArgs &a, unsigned grid, cudaStream_t s)
+{
+    if (mode == kHost) shade_kernel<kHost><<<grid, 256, 0, s>>>(a);
+    else shade_kernel<kExact><<<grid, 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) scatter_kernel(const __grid_constant__ ScatterArgs a)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint32_t tt = a.tile * a.tile;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < a.n_items; k += stride) {
+        const uint32_t m = (uint32_t)(k / tt), p = (uint32_t)(k % tt);
+        const uint32_t j = m * a.world + a.rank;
+        const uint32_t x = (j % a.tiles_x) * a.tile + p % a.tile;
+        const uint32_t y = (j / a.tiles_x) * a.tile + p / a.tile;
+        if (j >= a.n_tiles || x >= a.width || y >= a.height) continue;
+        const uint8_t *src = a.compact + k * a.elem;
+        uint8_t *dst = a.image + ((uint64_t)y * a.width + x) * a.elem;
+        if (a.elem % 4 == 0) {
+            for (uint32_t b = 0; b < a.elem; b += 4) *reinterpret_cast<uint32_t *>(dst + b) = *reinterpret_cast<const uint32_t *>(src + b);
+        } else {
+            for (uint32_t b = 0; b < a.elem; ++b) dst[b] = src[b];
+        }
+    }
+}
+
+cudaError_t launch_scatter(const ScatterArgs &a, unsigned grid, cudaStream_t s)
+{
+    scatter_kernel<<<grid, 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+// ---- roofline probes ------------------------------------------------------------
+// Register-only loops: 8 independent chains per thread so the pipes, not latency,
+// set the pace.  The kernels also report elapsed SM cycles so the caller can turn
+// the event time into the clock the SMs actually ran at.
+__global__ void __launch_bounds__(256) probe_ffma_kernel(float *sink, float b, float c, int iters, long long *cycles)
+{
+    float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f;
+    float x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = __fmaf_rn(x0, b, c); x1 = __fmaf_rn(x1, b, c); x2 = __fmaf_rn(x2, b, c); x3 = __fmaf_rn(x3, b, c);
+            x4 = __fmaf_rn(x4, b, c); x5 = __fmaf_rn(x5, b, c); x6 = __fmaf_rn(x6, b, c); x7 = __fmaf_rn(x7, b, c);
+        }
+    }
+    const long long t1 = clock64();
+    sink[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+__global__ void __launch_bounds__(256) probe_mufu_kernel(float *sink, float b, float c, int iters, long long *cycles)
+{
+    float x0 = 1.5f + threadIdx.x * 1e-3f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f;
+    float x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            // one MUFU.LG2 + one FFMA per link, the mix of the exact-mode exponent step
+            x0 = __fmaf_rn(ArithDev::lg2(x0), b, c); x1 = __fmaf_rn(ArithDev::lg2(x1), b, c);
+            x2 = __fmaf_rn(ArithDev::lg2(x2), b, c); x3 = __fmaf_rn(ArithDev::lg2(x3), b, c);
+            x4 = __fmaf_rn(ArithDev::lg2(x4), b, c); x5 = __fmaf_rn(ArithDev::lg2(x5), b, c);
+            x6 = __fmaf_rn(ArithDev::lg2(x6), b, c); x7 = __fmaf_rn(ArithDev::lg2(x7), b, c);
+        }
+    }
+    const long long t1 = clock64();
+    sink[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+cudaError_t probe_peaks(double *ffma_ops, double *mufu_ops, double *clock_hz, int *sms)
+{
+    int dev = 0, n_sm = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    const int blocks = n_sm * 8, threads = 256;
+    float *sink = nullptr;
+    long long *cyc = nullptr;
+    if ((e = cudaMalloc(&sink, sizeof(float) * blocks * threads)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&cyc, sizeof(long long) * blocks)) != cudaSuccess) { cudaFree(sink); return e; }
+    cudaEvent_t ev0, ev1;
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    double best_f = 0, best_m = 0, clk = 0;
+    const int it_f = 4096, it_m = 1024;
+    for (int rep = 0; rep < 4; ++rep) {
+        float ms = 0;
+        cudaEventRecord(ev0);
+        probe_ffma_kernel<<<blocks, threads>>>(sink, 0.999f, 0.001f, it_f, cyc);
+        cudaEventRecord(ev1);
+        if ((e = cudaEventSynchronize(ev1)) != cudaSuccess) break;
+        cudaEventElapsedTime(&ms, ev0, ev1);
+        const double ops = (double)blocks * threads * it_f * 64.0 / (ms * 1e-3);
+        if (rep && ops > best_f) {
+            best_f = ops;
+            long long c0 = 0;
+            cudaMemcpy(&c0, cyc, sizeof c0, cudaMemcpyDeviceToHost);
+            // a block's share of the run: blocks are all resident at once (8 per SM)
+            clk = (double)c0 / (ms * 1e-3);
+        }
+        cudaEventRecord(ev0);
+        probe_mufu_kernel<<<blocks, threads>>>(sink, 0.37f, 2.5f, it_m, cyc);
+        cudaEventRecord(ev1);
+        if ((e = cudaEventSynchronize(ev1)) != cudaSuccess) break;
+        cudaEventElapsedTime(&ms, ev0, ev1);
+        const double mops = (double)blocks * threads * it_m * 32.0 / (ms * 1e-3);
+        if (rep && mops > best_m) best_m = mops;
+    }
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    cudaFree(sink);
+    cudaFree(cyc);
+    if (e != cudaSuccess) return e;
+    *ffma_ops = best_f;
+    *mufu_ops = best_m;
+    *clock_hz = clk;
+    *sms = n_sm;
+    return cudaSuccess;
+}
+
+} // namespace lyap

@@ -1,0 +1,43 @@
+// tu_bake_impl.cuh -- included by tu_bake_<mode>.cu with LYAP_TU_MODE / LYAP_TU_NAME set.
+#include "launch.hpp"
+
+namespace lyap {
+
+#define LYAP_CAT2(a, b) a##b
+#define LYAP_CAT(a, b) LYAP_CAT2(a, b)
+
+cudaError_t LYAP_CAT(launch_bake_, LYAP_TU_NAME)(int P, const BakeArgs &a, unsigned grid, cudaStream_t s)
+{
+    switch (P) {
+#define X(p) case p: bake_kernel<LYAP_TU_MODE, p><<<grid, 256, 0, s>>>(a); break;
+        LYAP_PERIODS(X)
+#undef X
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t LYAP_CAT(launch_points_, LYAP_TU_NAME)(int P, const PointsArgs &a, unsigned grid, cudaStream_t s)
+{
+    switch (P) {
+#define X(p) case p: points_kernel<LYAP_TU_MODE, p><<<grid, 256, 0, s>>>(a); break;
+        LYAP_PERIODS(X)
+#undef X
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+int LYAP_CAT(bake_blocks_per_sm_, LYAP_TU_NAME)(int P)
+{
+    int n = 0;
+    switch (P) {
+#define X(p) case p: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, bake_kernel<LYAP_TU_MODE, p>, 256, 0); break;
+        LYAP_PERIODS(X)
+#undef X
+    default: break;
+    }
+    return n;
+}
+
+} // namespace lyap

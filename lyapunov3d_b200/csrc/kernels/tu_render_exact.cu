@@ -1,0 +1,4 @@
+// render kernels, exponent mode exact: all sequence-period instantiations.
+#define LYAP_TU_MODE kExact
+#define LYAP_TU_NAME exact
+#include "tu_render_impl.cuh"

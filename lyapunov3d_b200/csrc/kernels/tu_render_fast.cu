@@ -1,0 +1,4 @@
+// render kernels, exponent mode fast: all sequence-period instantiations.
+#define LYAP_TU_MODE kFast
+#define LYAP_TU_NAME fast
+#include "tu_render_impl.cuh"

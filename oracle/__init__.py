@@ -205,3 +205,39 @@ class RefHost(_HostChecker):
         vol = np.zeros((nz, ny, nx), np.float32)
         self.lib.ref_bake_slab(_p(vol), C.byref(prm), _p(seq), C.c_uint32(nx), C.c_uint32(ny), C.c_uint32(nz), C.c_uint32(z0), C.c_uint32(z1))
         return vol
+
+
+class RefCuda:
+    """The unmodified reference kernel.cu, nvcc --use_fast_math -arch=sm_100 (needs a GPU)."""
+
+    def __init__(self):
+        if not os.path.exists(REF_CUDA_SO):
+            raise FileNotFoundError(REF_CUDA_SO)
+        self.lib = C.CDLL(REF_CUDA_SO)
+
+    @staticmethod
+    def available():
+        return os.path.exists(REF_CUDA_SO)
+
+    def render(self, cam, prm, seq, lights, n_lights, w, h, reps=1):
+        """Returns (rgba[h,w,4], points[h,w], best kernel ms)."""
+        seq = _seq_array(seq)
+        rgba = np.zeros((h, w, 4), np.uint8)
+        pts = np.zeros((h, w), POINT_DTYPE)
+        ms = C.c_float(0)
+        rc = self.lib.ref_cuda_render(_p(rgba), _p(pts), C.byref(cam), C.byref(prm), _p(seq), C.c_size_t(seq.size),
+                                      C.byref(lights), C.c_uint32(n_lights), C.c_uint32(w), C.c_uint32(h),
+                                      C.c_int(reps), C.byref(ms))
+        if rc != 0:
+            raise RuntimeError(f"ref_cuda_render failed: cudaError {rc}")
+        return rgba, pts, ms.value
+
+    def bake(self, prm, seq, n, reps=1, want_output=True):
+        seq = _seq_array(seq)
+        vol = np.zeros((n, n, n), np.float32) if want_output else None
+        ms = C.c_float(0)
+        rc = self.lib.ref_cuda_bake(_p(vol) if want_output else None, C.byref(prm), _p(seq), C.c_size_t(seq.size),
+                                    C.c_uint32(n), C.c_int(reps), C.byref(ms))
+        if rc != 0:
+            raise RuntimeError(f"ref_cuda_bake failed: {rc}")
+        return vol, ms.value

@@ -1,0 +1,127 @@
+"""Host scene layer of the product library (params / scene / camera path / file
+formats) against the reference's golden outputs, and the C-ABI surface itself.
+CPU only: nothing here launches a kernel."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import lyapunov3d_b200 as lp
+from helpers import from_raw
+from lyapunov3d_b200 import api
+from lyapunov3d_b200.structs import Cam, LightArray, Params, clone, struct_bytes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    """Every function include/lyap/abi.h declares must be exported by the built .so."""
+    hdr = open(os.path.join(ROOT, "include", "lyap", "abi.h")).read()
+    names = sorted(set(re.findall(r"\b(lyap_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 25
+    L = api.lib()
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    assert b"sm_100a" in L.lyap_version()
+
+
+def test_params_init_matches_reference(golden):
+    g = golden["scene"]
+    prm, cam, lights, n, seq, size = lp.params_init()
+    assert struct_bytes(prm) == g["prm"].tobytes()
+    assert struct_bytes(cam) == g["cam"].tobytes()
+    assert struct_bytes(lights) == g["lights"].tobytes()
+    assert (n, seq, list(size)) == (int(g["n_lights"]), str(g["sequence"]), list(g["default_size"]))
+
+
+def test_sequence_parser(golden):
+    g = golden["scene"]
+    for k, s in enumerate(g["seq_strings"]):
+        assert lp.scene_convert_sequence(str(s)).tolist() == g[f"seq_{k}"].tolist(), s
+    with pytest.raises(lp.LyapError):
+        lp.scene_convert_sequence("ABX")          # reference exits; the library reports
+    with pytest.raises(lp.LyapError):
+        lp.scene_convert_sequence("")
+
+
+def test_camera_lights_and_path(golden):
+    g = golden["scene"]
+    cam = from_raw(Cam, g["cam"])
+    for k, (w, h, d) in enumerate(g["cam_sizes"]):
+        c = clone(cam)
+        lp.scene_cam_recalculate(c, int(w), int(h), int(d))
+        assert struct_bytes(c) == g[f"cam_recalc_{k}"].tobytes(), (w, h, d)
+    lights = from_raw(LightArray, g["lights"])
+    lp.scene_lights_recalculate(lights, int(g["n_lights"]))
+    assert struct_bytes(lights) == g["lights_recalc"].tobytes()
+    for i, want in zip(g["campath_i"], g["campath_cams"]):
+        c = clone(cam)
+        lp.campath_orbit(float(i), c)
+        assert struct_bytes(c) == want.tobytes(), i
+
+
+def test_campath_frames_agree_with_oracle(oracle):
+    """120-frame orbit (BASELINE config 5): frame f of n uses i = ease(f/(n-1)) rounded
+    to 15 significant digits, as scale.pl's string interpolation would."""
+    _, cam, *_ = lp.params_init()
+    for f in (0, 1, 37, 59, 60, 118, 119):
+        a, b = clone(cam), clone(cam)
+        lp.campath_frame(f, 120, a)
+        i = float("%.15g" % oracle.ease(f / 119.0))
+        oracle.campath(i, b)
+        assert struct_bytes(a) == struct_bytes(b), f
+    last = clone(cam)
+    lp.campath_frame(119, 120, last)
+    assert struct_bytes(last) == struct_bytes(cam)   # the shipped params.cu is the final frame
+
+
+def test_plan_picks_period_instantiations():
+    conv = lp.scene_convert_sequence
+    assert api.plan_period(conv("BCABA"), 18, 1008) == 5
+    assert api.plan_period(conv("A6B6C6"), 72, 4032) == 21
+    assert api.plan_period(conv("ABAB"), 18, 1008) == 2          # reduced to its true period
+    assert api.plan_period(conv("A8B8"), 18, 1008) == 18
+    assert api.plan_period(conv("A9B9C9D9"), 18, 1008) == 0      # 40 symbols: generic loop
+    assert api.plan_period(conv("A8B7"), 18, 1008) == 0          # period 17 has no instantiation
+    assert api.plan_period(np.array([0, 5, -1], np.int32), 1, 1) == -1
+    assert api.plan_period(np.array([-1], np.int32), 1, 1) == -1
+    assert api.tile_count(1920, 1080, 8, 0, 1) == 240 * 135 * 64
+    assert sum(api.tile_count(100, 50, 8, r, 3) for r in range(3)) == 13 * 7 * 64
+
+
+def test_file_formats(tmp_path, golden):
+    rgba = golden["frames"]["default_40x24_rgba"]
+    h, w = rgba.shape[:2]
+    ppm = tmp_path / "f.ppm"
+    api.write_ppm(str(ppm), rgba)
+    # what the reference's save_ppm loop prints (lyap_interactive.cu:595-606)
+    want = "P3\n%d %d\n%d\n" % (w, h, 255) + "".join("%3d %3d %3d " % (p[0], p[1], p[2]) for p in rgba.reshape(-1, 4)) + "\n"
+    assert ppm.read_text() == want
+    png = tmp_path / "f.png"
+    api.write_png(str(png), rgba)
+    from PIL import Image
+    assert np.array_equal(np.asarray(Image.open(png).convert("RGB")), rgba[..., :3])
+    raw = tmp_path / "p.raw"
+    pts = golden["frames"]["default_40x24_points"]
+    api.write_raw(str(raw), pts)
+    assert raw.read_bytes() == pts.tobytes()
+    prm, cam, *_ = lp.params_init()
+    name = api.format_filename("Render", 1526604923, 8192, 8192, "BCABA", cam, prm)
+    assert name.startswith("Render_1526604923_8192x8192_BCABA_cx=3.9217899_cy=3.5029025_cz=3.5029025_")
+    assert name.endswith("_step=2_D=2.1_i=18,1008_d=4096_j=0.5_r=32_ot=-0.75")
+
+
+def test_no_cpu_fallback():
+    """Without a GPU the device entry points must refuse, not compute something else."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    prm, cam, lights, n, s, _ = lp.params_init()
+    with pytest.raises(lp.LyapError):
+        lp.bake(prm, lp.scene_convert_sequence(s), 8)
+    with pytest.raises(lp.LyapError):
+        lp.render(cam, prm, lp.scene_convert_sequence(s), lights, n, 16, 16)
+    with pytest.raises(lp.LyapError):
+        lp.bake_host(prm, lp.scene_convert_sequence(s), 8)
