@@ -53,7 +53,9 @@ const char *lyap_error_string(int code);
 
 /* Tuning / test knobs: "render_warps_per_sm" (persistent warps per SM, default 16),
  * "bake_blocks_per_sm" (cap; 0 = occupancy maximum), "force_generic" (1 = always use
- * the per-step-select exponent loop instead of a period instantiation). */
+ * the per-step-select exponent loop instead of a period instantiation),
+ * "emulate_ref_nvcc_normals" (test knob: reproduce the normals the reference's CUDA
+ * build produces under nvcc 12.9, where ls[] aliases lyap4d's abcd[]). */
 int lyap_set_option(const char *key, long value);
 /* Which unrolled-period instantiation a sequence runs on: its period's smallest
  * compiled multiple, 0 for the generic loop, -1 for an invalid sequence. */

@@ -25,6 +25,7 @@ namespace {
 std::atomic<long> g_force_generic{0};
 std::atomic<long> g_render_warps_per_sm{0};   // 0 = default
 std::atomic<long> g_bake_blocks_per_sm{0};    // 0 = occupancy maximum
+std::atomic<long> g_nvcc_normal_quirk{0};     // test knob: emulate the reference CUDA build's aliased normals
 
 constexpr int kDefaultRenderWarpsPerSM = 16;
 
@@ -141,6 +142,7 @@ int lyap_set_option(const char *key, long value)
     if (!strcmp(key, "force_generic")) g_force_generic = value;
     else if (!strcmp(key, "render_warps_per_sm")) g_render_warps_per_sm = value;
     else if (!strcmp(key, "bake_blocks_per_sm")) g_bake_blocks_per_sm = value;
+    else if (!strcmp(key, "emulate_ref_nvcc_normals")) g_nvcc_normal_quirk = value;
     else return LYAP_ERR_BAD_ARGUMENT;
     return LYAP_OK;
 }
@@ -190,6 +192,7 @@ int lyap_render_tiles(lyap_rgba *d_rgba, lyap_point *d_points, const lyap_cam *c
     a.rank = rank;
     a.world = world;
     a.compact = compact ? 1u : 0u;
+    a.nvcc_normal_quirk = g_nvcc_normal_quirk.load() ? 1u : 0u;
     a.n_items = lyap_tile_count(width, height, tile, rank, world);
     a.evals = d_evals;
     if (a.n_items == 0) return LYAP_OK;

@@ -29,9 +29,12 @@ struct BakeArgs {
 template <int MODE>
 __device__ __forceinline__ float voxel_coord(uint32_t i, uint32_t n)
 {
-    // a = 4.0f * (float)x / (float)N  (kernel.cu:527-529); device build: mul.ftz then div.approx
-    if constexpr (MODE == kHost) return __fdiv_rn(__fmul_rn(4.0f, __uint2float_rn(i)), __uint2float_rn(n));
-    else return ArithDev::div(ArithDev::mul(__uint2float_rn(i), 4.0f), __uint2float_rn(n));
+    // a = 4.0f * (float)x / (float)N  (kernel.cu:527-529).  The reference's device build divides
+    // with div.approx (kExact mirrors it: bit parity with the reference kernel on any grid);
+    // its host build divides exactly (kHost, and kFast so that it tracks the CPU oracle on
+    // grids that are not powers of two -- in chaotic voxels one ulp of coordinate moves l).
+    if constexpr (MODE == kExact) return ArithDev::div(ArithDev::mul(__uint2float_rn(i), 4.0f), __uint2float_rn(n));
+    else return __fdiv_rn(__fmul_rn(4.0f, __uint2float_rn(i)), __uint2float_rn(n));
 }
 
 template <int MODE, int P>
@@ -89,6 +92,7 @@ struct RenderArgs {
     uint32_t tile, tiles_x, n_tiles;   // tile edge, tiles per row, tiles in the image
     uint32_t rank, world;              // this launch renders tiles j with j % world == rank
     uint32_t compact;                  // write outputs densely in work order
+    uint32_t nvcc_normal_quirk;        // test knob, see lyap_set_option("emulate_ref_nvcc_normals")
     unsigned long long n_items;        // work items of this rank: its tiles * tile^2
     unsigned long long *queue;         // next work item (zeroed before launch)
     unsigned long long *evals;         // optional: += exponent evaluations
@@ -168,6 +172,16 @@ __global__ void __launch_bounds__(kRenderThreads) render_kernel(const __grid_con
             ++evals;
             const RayEvent ev = ray_advance<A>(st, l, a.prm);
             if (ev != kContinue) {
+                if (ev == kHit) {
+                    if (a.nvcc_normal_quirk) {
+                        // What the reference's CUDA build computes under nvcc 12.9: ls[] shares its
+                        // stack slot with lyap4d's abcd[], so ls[0..3] end up holding the last
+                        // sample point and d (DESIGN.md "reference build defect").  Test knob only.
+                        st.Nx = A::sub(st.Py, st.Px);
+                        st.Ny = A::sub(a.prm.d, A::add(st.mag, st.Pz));
+                    }
+                    normalize3<A>(st.Nx, st.Ny, st.Nz);
+                }
                 finish_pixel<A>(a, st, ev == kHit);
                 st.phase = kNeedRay;
             }

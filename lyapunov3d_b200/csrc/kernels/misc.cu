@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(256) probe_ffma_kernel(float *sink, float b, f
     float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f;
     float x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
     const long long t0 = clock64();
+    if (t0 == 0x7fffffffffffffffLL) x0 = 0.f;   // order the loop after the first clock read
 #pragma unroll 1
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
@@ -55,8 +56,10 @@ __global__ void __launch_bounds__(256) probe_ffma_kernel(float *sink, float b, f
             x4 = __fmaf_rn(x4, b, c); x5 = __fmaf_rn(x5, b, c); x6 = __fmaf_rn(x6, b, c); x7 = __fmaf_rn(x7, b, c);
         }
     }
-    const long long t1 = clock64();
-    sink[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    const float sum = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    sink[blockIdx.x * blockDim.x + threadIdx.x] = sum;
+    long long t1 = clock64();
+    if (sum == 123.456f) t1 = 0;                // and the second read after the results exist
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
@@ -65,6 +68,7 @@ __global__ void __launch_bounds__(256) probe_mufu_kernel(float *sink, float b, f
     float x0 = 1.5f + threadIdx.x * 1e-3f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f;
     float x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
     const long long t0 = clock64();
+    if (t0 == 0x7fffffffffffffffLL) x0 = 0.f;
 #pragma unroll 1
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
@@ -76,8 +80,10 @@ __global__ void __launch_bounds__(256) probe_mufu_kernel(float *sink, float b, f
             x6 = __fmaf_rn(ArithDev::lg2(x6), b, c); x7 = __fmaf_rn(ArithDev::lg2(x7), b, c);
         }
     }
-    const long long t1 = clock64();
-    sink[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    const float sum = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    sink[blockIdx.x * blockDim.x + threadIdx.x] = sum;
+    long long t1 = clock64();
+    if (sum == 123.456f) t1 = 0;                // and the second read after the results exist
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 

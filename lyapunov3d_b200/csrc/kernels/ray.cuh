@@ -313,8 +313,8 @@ __device__ __forceinline__ RayEvent refine_begin(RayState &st, const lyap_params
     return kContinue;
 }
 
-// Consume the exponent `l` of the pending sample.  On kHit st.{P,N,a,c,l} hold the
-// LyapPoint fields (kernel.cu:479-483).
+// Consume the exponent `l` of the pending sample.  On kHit st.{P,a,c,l} hold the
+// LyapPoint fields (kernel.cu:479-483) and st.N the un-normalised central differences.
 template <class A>
 __device__ __forceinline__ RayEvent ray_advance(RayState &st, float l, const lyap_params &prm)
 {
@@ -372,8 +372,7 @@ __device__ __forceinline__ RayEvent ray_advance(RayState &st, float l, const lya
         return kContinue;
     case kNormal5:
         st.Nz = A::sub(l, st.lprev);
-        normalize3<A>(st.Nx, st.Ny, st.Nz);   // :473
-        return kHit;
+        return kHit;   // caller normalises N (:473)
     default:
         return kContinue;
     }
