@@ -29,6 +29,8 @@ CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-I", os.path.jo
 
 CU = ["abi.cu", "kernels/misc.cu"] + [f"kernels/tu_{k}_{m}.cu" for k in ("render", "bake") for m in ("exact", "fast", "host")]
 CPP = ["host/scene.cpp", "host/imageio.cpp"]
+APPS = ["lyap_render", "lyap_calculate"]
+BIN = os.path.join(PKG, "bin")
 
 
 def _sources():
@@ -74,6 +76,11 @@ def build(force=False, verbose=False, ptxas_info=False):
         for out in ex.map(lambda j: _run(j[1], verbose), jobs):
             logs.append(out)
     _run([NVCC] + ARCH + ["-shared", "-ccbin", HOSTCXX, "-o", LIB] + [j[0] for j in jobs] + ["-lz"], verbose)
+    # headless apps on top of the C ABI (the reference's two programs, re-hosted)
+    os.makedirs(BIN, exist_ok=True)
+    for app in APPS:
+        _run([HOSTCXX, "-O2", "-std=c++17", "-I", os.path.join(ROOT, "include"), os.path.join(CSRC, "apps", app + ".cpp"),
+              "-o", os.path.join(BIN, app), "-L", PKG, "-llyap_b200", "-Wl,-rpath,$ORIGIN/.."], verbose)
     if ptxas_info:
         return "\n".join(logs)
     return LIB

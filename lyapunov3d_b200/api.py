@@ -224,6 +224,19 @@ def bake(prm, seq, nx, ny=None, nz=None, z0=0, z1=None, mode="fast", dtype="f32"
     return out
 
 
+def bake_into(slab, slab_z0, prm, seq, nx, ny, nz, z0, z1, mode="fast", dtype="f32"):
+    """Bake planes z0..z1 of an [nz,ny,nx] volume into `slab`, a tensor whose plane 0 is plane
+    `slab_z0` of the volume (a rank that owns one z-slab need not allocate the whole volume)."""
+    torch = _torch()
+    seq = np.ascontiguousarray(seq, np.int32)
+    f16 = slab.dtype == torch.float16
+    assert slab.is_contiguous() and slab.shape[1:] == (ny, nx) and slab_z0 <= z0 and z1 - slab_z0 <= slab.shape[0]
+    base = slab.data_ptr() - slab_z0 * ny * nx * slab.element_size()
+    _check(lib().lyap_bake(base, F16 if f16 else F32, C.byref(prm), seq.ctypes.data, nx, ny, nz, z0, z1, _mode(mode),
+                           _stream_ptr(torch)), "lyap_bake")
+    return slab
+
+
 def exponent_points(xyz, prm, seq, mode="exact"):
     torch = _torch()
     seq = np.ascontiguousarray(seq, np.int32)
