@@ -116,9 +116,10 @@ def sample_rows(h, n):
     return [int((i + 0.5) * h / n) for i in range(n)]
 
 
-def cpu_sample(checker, counter, wl, scene, rows):
-    """Render the given rows on the CPU.  Returns (iterations, seconds).  `checker` does the
-    timed work; `counter` (the C restatement) counts evaluations if the checker cannot."""
+def cpu_sample(checker, counter, wl, scene, rows, known_calls=None):
+    """Render the given rows on the CPU.  Returns (iterations, seconds, calls).  `checker` does
+    the timed work; `counter` (the C restatement, bit-identical march) counts the exponent
+    evaluations once, outside the timed part, if the checker cannot count them itself."""
     prm, cam, lights, n_lights, seq = scene
     w, h = wl["w"], wl["h"]
     calls = 0
@@ -128,9 +129,10 @@ def cpu_sample(checker, counter, wl, scene, rows):
         calls += c or 0
     dt = time.perf_counter() - t0
     if not calls:
-        for y in rows:
-            calls += counter.render(cam, prm, seq, lights, n_lights, w, h, y0=y, y1=y + 1)[2]
-    return calls * (prm.settle + prm.accum), dt
+        calls = known_calls
+    if not calls:
+        calls = sum(counter.render(cam, prm, seq, lights, n_lights, w, h, y0=y, y1=y + 1)[2] for y in rows)
+    return calls * (prm.settle + prm.accum), dt, calls
 
 
 # --------------------------------------------------------------------- reference arm
@@ -147,13 +149,16 @@ def run_reference(args, wl, rank):
         checker, kind = RefHost(), "reference"
     else:
         checker, kind = port, "port"
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    port.set_threads(ncpu)       # torchrun exports OMP_NUM_THREADS=1
+    checker.set_threads(ncpu)
     scene = scene_for(wl, lp)
     rows = sample_rows(wl["h"], args.cpu_rows)
-    for _ in range(args.warmup):
-        cpu_sample(checker, port, wl, scene, rows[:1])
-    iters, secs = 0, 0.0
+    for _ in range(min(args.warmup, 1)):
+        cpu_sample(checker, port, wl, scene, rows[:1], known_calls=1)
+    iters, secs, calls = 0, 0.0, None
     for _ in range(args.steps):
-        i, s = cpu_sample(checker, port, wl, scene, rows)
+        i, s, calls = cpu_sample(checker, port, wl, scene, rows, known_calls=calls)
         iters += i
         secs += s
     val = iters / secs / 1e9
@@ -324,11 +329,12 @@ def main():
                 "hbm_gbs_sanity": out_bytes / (kernel_ms * 1e-3) / 1e9}
 
     cpu = None
-    if not args.no_cpu_baseline and "w" in wl:
+    if not args.no_cpu_baseline and "w" in wl and world == 1:
         from oracle import Oracle   # the checker, timed as the reported CPU baseline only
         port = Oracle()
+        port.set_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
         rows = sample_rows(wl["h"], args.cpu_rows)
-        it, secs = cpu_sample(port, port, wl, scene, rows)
+        it, secs, _ = cpu_sample(port, port, wl, scene, rows)
         cpu = {"value": it / secs / 1e9, "unit": "Giter/s", "cores": port.threads(), "kind": "port",
                "sample": f"{len(rows)} evenly spaced rows of the frame ({len(rows) * wl['w']} pixels), {secs:.1f} s"}
 

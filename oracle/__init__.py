@@ -131,6 +131,9 @@ class Oracle(_HostChecker):
     def threads(self):
         return self.lib.oracle_num_threads()
 
+    def set_threads(self, n):
+        self.lib.oracle_set_num_threads(int(n))
+
     def ease(self, t):
         return self.lib.oracle_ease_in_out_quart(t, 0.0, 1.0, 1.0)
 
@@ -181,6 +184,9 @@ class RefHost(_HostChecker):
     @staticmethod
     def available():
         return os.path.exists(REF_HOST_SO)
+
+    def set_threads(self, n):
+        self.lib.ref_set_num_threads(int(n))
 
     def raymarch(self, sx, sy, cam, prm, seq):
         seq = _seq_array(seq)

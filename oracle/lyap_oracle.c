@@ -505,6 +505,16 @@ void oracle_bake_slab(float *exps, const lyap_params *prm, const int32_t *seq,
     }
 }
 
+/* torchrun exports OMP_NUM_THREADS=1; the CPU baseline wants every host core. */
+void oracle_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int oracle_num_threads(void)
 {
 #ifdef _OPENMP

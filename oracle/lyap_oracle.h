@@ -51,6 +51,7 @@ uint64_t oracle_render_pixels(lyap_rgba *rgba, lyap_point *points, const lyap_ca
 void oracle_bake_slab(float *exps, const lyap_params *prm, const int32_t *seq,
                       uint32_t nx, uint32_t ny, uint32_t nz, uint32_t z0, uint32_t z1);
 int oracle_num_threads(void);
+void oracle_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

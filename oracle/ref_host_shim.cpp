@@ -41,7 +41,18 @@ static inline unsigned int __umul24(unsigned int a, unsigned int b)
 #include "scene.cu"
 #include "params.cu"
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
 extern "C" {
+
+void ref_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#endif
+}
 
 size_t ref_sizeof_camlight(void) { return sizeof(LyapCam); }
 size_t ref_sizeof_params(void) { return sizeof(LyapParams); }

@@ -367,3 +367,20 @@ def test_full_size_bake_properties(scene):
     finite = vol[~vol.isnan()]
     assert -9.0 < float(finite.min()) and float(finite.max()) < 1.0
     assert bool(vol[0].isnan().all()) and bool(vol[:, 0].isnan().all()) and bool(vol[:, :, 0].isnan().all())
+
+
+def test_multi_gpu_shards_equal_single_gpu():
+    """With >= 2 GPUs on the box: tools/gpu_dist_check.py under torchrun (NCCL) asserts that the
+    tile-sharded frame, the z-slab bake and the frame-sharded orbit equal the single-GPU results."""
+    need_gpu()
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("single-GPU box: partition invariance is covered by test_tile_partition_is_bit_identical")
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(n, 8)}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "gpu_dist_check.py")],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "dist correctness ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
