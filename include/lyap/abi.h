@@ -162,6 +162,8 @@ int lyap_format_filename(char *out, size_t cap, const char *prefix, unsigned lon
  * Roofline probes: register-only FFMA and MUFU.LG2 loops.  Returns achieved
  * lane-operations per second over `iters` inner iterations on the current device.
  * ------------------------------------------------------------------------- */
+/* Same loop with packed fma.rn.f32x2 (FFMA2): scalar-equivalent lane-operations per second. */
+int lyap_probe_ffma2(double *packed_ffma_lane_ops_per_s);
 int lyap_probe_peaks(double *ffma_lane_ops_per_s, double *mufu_lane_ops_per_s, double *sm_clock_hz_est, int *sm_count);
 
 #ifdef __cplusplus

@@ -69,6 +69,7 @@ def lib():
     L.lyap_write_raw.argtypes = [C.c_char_p, vp, u64]
     L.lyap_format_filename.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_ulong, u32, u32, C.c_char_p, vp, vp]
     L.lyap_probe_peaks.argtypes = [vp, vp, vp, vp]
+    L.lyap_probe_ffma2.argtypes = [vp]
     _lib = L
     return L
 
@@ -305,4 +306,6 @@ def probe_peaks():
     _torch()
     f, m, c, n = C.c_double(), C.c_double(), C.c_double(), C.c_int()
     _check(lib().lyap_probe_peaks(C.byref(f), C.byref(m), C.byref(c), C.byref(n)), "lyap_probe_peaks")
-    return {"ffma_lane_ops_per_s": f.value, "mufu_lane_ops_per_s": m.value, "sm_clock_hz": c.value, "sm_count": n.value}
+    f2 = C.c_double()
+    _check(lib().lyap_probe_ffma2(C.byref(f2)), "lyap_probe_ffma2")
+    return {"ffma2_lane_ops_per_s": f2.value, "ffma_lane_ops_per_s": f.value, "mufu_lane_ops_per_s": m.value, "sm_clock_hz": c.value, "sm_count": n.value}

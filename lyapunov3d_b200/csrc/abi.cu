@@ -284,12 +284,24 @@ int lyap_bake(void *d_exps, int dtype, const lyap_params *prm, const int32_t *se
     if (per_sm <= 0) return (int)cudaErrorLaunchOutOfResources;
     const long cap = g_bake_blocks_per_sm.load();
     if (cap > 0 && cap < per_sm) per_sm = (int)cap;
-    const unsigned long long total = (unsigned long long)nx * ny * (z1 - z0);
-    unsigned long long grid = (unsigned long long)sc->sm_count * per_sm;
-    if (grid > (total + 255) / 256) grid = (total + 255) / 256;
+    // the kernel indexes a launch's voxels with 32 bits: cut tall slabs into z-chunks
+    const unsigned long long plane = (unsigned long long)nx * ny;
+    if (plane >= (1ull << 31)) return LYAP_ERR_BAD_ARGUMENT;
+    const uint32_t max_planes = (uint32_t)(((1ull << 31) - 1) / plane);
     cudaStream_t s = (cudaStream_t)stream;
-    e = by_mode(mode, [&] { return launch_bake_exact(P, a, (unsigned)grid, s); }, [&] { return launch_bake_fast(P, a, (unsigned)grid, s); },
-                [&] { return launch_bake_host(P, a, (unsigned)grid, s); });
+    for (uint32_t za = z0; za < z1; za += max_planes) {
+        const uint32_t zb = (z1 - za > max_planes) ? za + max_planes : z1;
+        a.z0 = za;
+        a.z1 = zb;
+        const unsigned long long total = plane * (zb - za);
+        const unsigned long long per_thread = (mode == LYAP_MODE_FAST) ? 2 : 1;
+        unsigned long long grid = (unsigned long long)sc->sm_count * per_sm;
+        const unsigned long long need = (total / per_thread + 255) / 256 + 1;
+        if (grid > need) grid = need;
+        e = by_mode(mode, [&] { return launch_bake_exact(P, a, (unsigned)grid, s); }, [&] { return launch_bake_fast(P, a, (unsigned)grid, s); },
+                    [&] { return launch_bake_host(P, a, (unsigned)grid, s); });
+        if (e != cudaSuccess) break;
+    }
     return (int)e;
 }
 
@@ -386,6 +398,15 @@ int lyap_bake_host(void *h_exps, int dtype, const lyap_params *prm, const int32_
     if (s) cudaStreamDestroy(s);
     if (rc != LYAP_OK) return rc;
     return (int)e;
+}
+
+int lyap_probe_ffma2(double *packed_ffma_lane_ops_per_s)
+{
+    double v = 0;
+    const cudaError_t e = probe_ffma2(&v);
+    if (e != cudaSuccess) return (int)e;
+    if (packed_ffma_lane_ops_per_s) *packed_ffma_lane_ops_per_s = v;
+    return LYAP_OK;
 }
 
 int lyap_probe_peaks(double *ffma_lane_ops_per_s, double *mufu_lane_ops_per_s, double *sm_clock_hz_est, int *sm_count)

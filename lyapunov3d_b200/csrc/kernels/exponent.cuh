@@ -229,4 +229,159 @@ __device__ __forceinline__ float exponent(const SeqPlan &sp, float x, float y, f
     return l;
 }
 
+// ------------------------------------------------- two samples per lane (packed f32x2)
+// sm_100 has packed single-precision FMA/MUL on 64-bit register pairs (FFMA2/FMUL2).  They
+// occupy one ISSUE slot for two lanes' worth of work, which matters here because the fast
+// exponent is issue-bound (four FP32 instructions per step plus folds and loop control on a
+// one-instruction-per-clock scheduler).  The packed forms take no negate/abs modifiers, so
+// the trajectory is carried as w = -v:  p' = r*w = -(r*v);  w' = fma(p', w, p') = -(p - p*v),
+// bit-identical to the scalar form by the sign symmetry of round-to-nearest; the derivative
+// factor is q = fma(2, w', 1) = 1 - 2v' and its sign is simply dropped at fold time.
+typedef unsigned long long f32x2;
+
+__device__ __forceinline__ f32x2 pack2(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+struct AccumFast2 {
+    static constexpr int kBias = Accum<kFast>::kBias;
+    f32x2 prod;
+    int esum0, esum1, emin0, emin1;
+    __device__ __forceinline__ void init()
+    {
+        const float b = __int_as_float((127 + kBias) << 23);
+        prod = pack2(b, b);
+        esum0 = esum1 = 0;
+        emin0 = emin1 = 255;
+    }
+    __device__ __forceinline__ void step(f32x2 r, f32x2 &w, f32x2 two, f32x2 one)
+    {
+        const f32x2 p = mul2(r, w);
+        w = fma2(p, w, p);
+        prod = mul2(prod, fma2(two, w, one));
+    }
+    __device__ __forceinline__ void renorm()
+    {
+        float a, b;
+        unpack2(prod, a, b);
+        const int ba = __float_as_int(a) & 0x7fffffff, bb = __float_as_int(b) & 0x7fffffff;
+        const int ea = ba >> 23, eb = bb >> 23;
+        esum0 += ea - (127 + kBias);
+        esum1 += eb - (127 + kBias);
+        emin0 = min(emin0, ea);
+        emin1 = min(emin1, eb);
+        prod = pack2(__int_as_float((ba & 0x007fffff) | ((127 + kBias) << 23)),
+                     __int_as_float((bb & 0x007fffff) | ((127 + kBias) << 23)));
+    }
+};
+
+__device__ __forceinline__ float fast_finish(const SeqPlan &sp, int esum, int emin, float prod, float x, float y, float z,
+                                             float d, float v)
+{
+    const float mant = __int_as_float((__float_as_int(prod) & 0x007fffff) | 0x3f800000);
+    double l2 = (double)esum + (double)__log2f(mant);
+    if (sp.cnt[0]) l2 += (double)sp.cnt[0] * (double)__log2f(fabsf(x));
+    if (sp.cnt[1]) l2 += (double)sp.cnt[1] * (double)__log2f(fabsf(y));
+    if (sp.cnt[2]) l2 += (double)sp.cnt[2] * (double)__log2f(fabsf(z));
+    if (sp.cnt[3]) l2 += (double)sp.cnt[3] * (double)__log2f(fabsf(d));
+    const float l = (float)(l2 * (0.6931471805599453 / (double)sp.accum));
+    const bool bad = (emin == 0) || !is_finite(v) || !is_finite(l);
+    return bad ? quiet_nan() : l;
+}
+
+// Exponents of two sample points A and B in one pass (fast mode only).
+template <int P>
+__device__ __forceinline__ void exponent_fast2(const SeqPlan &sp, float xa, float ya, float za, float xb, float yb, float zb,
+                                               float d, float &la, float &lb)
+{
+    const f32x2 two = pack2(2.0f, 2.0f), one = pack2(1.0f, 1.0f);
+    f32x2 w = pack2(-0.5f, -0.5f);
+    AccumFast2 acc;
+    acc.init();
+    float vsa, vsb;
+    auto rpair = [&](uint32_t s) { return pack2(sel4(s, xa, ya, za, d), sel4(s, xb, yb, zb, d)); };
+    auto settle_step = [&](f32x2 r) {
+        const f32x2 p = mul2(r, w);
+        w = fma2(p, w, p);
+    };
+
+    if constexpr (P > 0) {
+        f32x2 r[P];
+#pragma unroll
+        for (int k = 0; k < P; k++) r[k] = rpair(sp.rot[k]);
+        for (uint32_t n = 0; n < sp.settle_head; n++) settle_step(rpair(sp.sym[n]));
+#pragma unroll 1
+        for (uint32_t i = 0; i < sp.settle_periods; i++) {
+#pragma unroll
+            for (int k = 0; k < P; k++) settle_step(r[k]);
+        }
+        unpack2(w, vsa, vsb);
+        constexpr int U = PeriodUnroll<P>::U;
+        const uint32_t groups = sp.accum_periods / U;
+#pragma unroll 1
+        for (uint32_t g = 0; g < groups; g++) {
+#pragma unroll
+            for (int s = 0; s < U * P; s++) {
+                acc.step(r[s % P], w, two, one);
+                if ((s + 1) % Accum<kFast>::kFoldEvery == 0 || s + 1 == U * P) acc.renorm();
+            }
+        }
+        if constexpr (U > 1) {
+#pragma unroll 1
+            for (uint32_t i = groups * U; i < sp.accum_periods; i++) {
+#pragma unroll
+                for (int k = 0; k < P; k++) acc.step(r[k], w, two, one);
+                acc.renorm();
+            }
+        }
+#pragma unroll 1
+        for (uint32_t n = 0; n < sp.accum_tail; n++) {
+            acc.step(rpair(sp.rot[n]), w, two, one);
+            if ((n & 7) == 7) acc.renorm();
+        }
+    } else {
+        uint32_t pos = 0;
+#pragma unroll 1
+        for (uint32_t n = 0; n < sp.settle; n++) {
+            settle_step(rpair(sp.sym[pos]));
+            pos = (pos + 1 == sp.len) ? 0 : pos + 1;
+        }
+        unpack2(w, vsa, vsb);
+#pragma unroll 1
+        for (uint32_t n = 0; n < sp.accum; n++) {
+            acc.step(rpair(sp.sym[pos]), w, two, one);
+            pos = (pos + 1 == sp.len) ? 0 : pos + 1;
+            if ((n & 7) == 7) acc.renorm();
+        }
+    }
+    acc.renorm();
+    float pa, pb, wa, wb;
+    unpack2(acc.prod, pa, pb);
+    unpack2(w, wa, wb);
+    la = fast_finish(sp, acc.esum0, acc.emin0, pa, xa, ya, za, d, wa);
+    lb = fast_finish(sp, acc.esum1, acc.emin1, pb, xb, yb, zb, d, wb);
+    const float zero = __fdiv_rn(0.0f, __uint2float_rn(sp.accum));
+    if (vsa == -0.5f) la = zero;   // w == -0.5 <=> v == 0.5 after settling (kernel.cu:138)
+    if (vsb == -0.5f) lb = zero;
+}
+
 } // namespace lyap

@@ -37,22 +37,56 @@ __device__ __forceinline__ float voxel_coord(uint32_t i, uint32_t n)
     else return __fdiv_rn(__fmul_rn(4.0f, __uint2float_rn(i)), __uint2float_rn(n));
 }
 
+__device__ __forceinline__ void store_voxel(const BakeArgs &a, uint64_t idx, float l)
+{
+    if (a.f16) reinterpret_cast<__half *>(a.out)[idx] = __float2half_rn(l);
+    else reinterpret_cast<float *>(a.out)[idx] = l;
+}
+
+// Index arithmetic is 32-bit: lyap_bake() splits a slab into launches of < 2^31 voxels.
 template <int MODE, int P>
 __global__ void __launch_bounds__(256) bake_kernel(const __grid_constant__ BakeArgs a)
 {
+    typedef uint32_t IdxT;
     if constexpr (MODE == kHost) hostlog_init();
-    const uint64_t plane = (uint64_t)a.nx * a.ny;
-    const uint64_t total = plane * (a.z1 - a.z0);
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const uint32_t z = a.z0 + (uint32_t)(i / plane);
-        const uint32_t rem = (uint32_t)(i % plane);
-        const uint32_t y = rem / a.nx, x = rem % a.nx;
-        const float l = exponent<MODE, P>(a.plan, voxel_coord<MODE>(x, a.nx), voxel_coord<MODE>(y, a.ny),
-                                          voxel_coord<MODE>(z, a.nz), a.d);
-        const uint64_t idx = (uint64_t)z * plane + rem;
-        if (a.f16) reinterpret_cast<__half *>(a.out)[idx] = __float2half_rn(l);
-        else reinterpret_cast<float *>(a.out)[idx] = l;
+    const IdxT nx = a.nx;
+    const IdxT plane = (IdxT)a.nx * (IdxT)a.ny;
+    const IdxT total = plane * (IdxT)(a.z1 - a.z0);
+    const IdxT stride = (IdxT)gridDim.x * blockDim.x;
+    const uint64_t base = (uint64_t)a.z0 * a.nx * a.ny;
+    if constexpr (MODE == kFast) {
+        // two x-adjacent voxels per lane through the packed evaluator: a warp covers 64
+        // consecutive voxels and stores 256 contiguous bytes (FP32)
+        const IdxT pairs = total / 2 + (total & 1);
+        for (IdxT k = (IdxT)blockIdx.x * blockDim.x + threadIdx.x; k < pairs; k += stride) {
+            const IdxT i0 = 2 * k, i1 = (2 * k + 1 < total) ? 2 * k + 1 : 2 * k;
+            const IdxT q0 = i0 / plane, r0 = i0 - q0 * plane, y0 = r0 / nx, x0 = r0 - y0 * nx;
+            IdxT q1 = q0, y1 = y0, x1 = x0;
+            if (i1 != i0) {
+                x1 = x0 + 1;
+                if (x1 == nx) { x1 = 0; y1 = y0 + 1; if (y1 == (IdxT)a.ny) { y1 = 0; q1 = q0 + 1; } }
+            }
+            float l0, l1;
+            exponent_fast2<P>(a.plan, voxel_coord<MODE>((uint32_t)x0, a.nx), voxel_coord<MODE>((uint32_t)y0, a.ny),
+                              voxel_coord<MODE>(a.z0 + (uint32_t)q0, a.nz), voxel_coord<MODE>((uint32_t)x1, a.nx),
+                              voxel_coord<MODE>((uint32_t)y1, a.ny), voxel_coord<MODE>(a.z0 + (uint32_t)q1, a.nz), a.d, l0, l1);
+            const uint64_t o0 = base + i0;
+            if (!a.f16 && i1 != i0 && (o0 & 1) == 0) {
+                reinterpret_cast<float2 *>(a.out)[o0 >> 1] = make_float2(l0, l1);
+            } else if (a.f16 && i1 != i0 && (o0 & 1) == 0) {
+                reinterpret_cast<__half2 *>(a.out)[o0 >> 1] = __floats2half2_rn(l0, l1);
+            } else {
+                store_voxel(a, o0, l0);
+                if (i1 != i0) store_voxel(a, o0 + 1, l1);
+            }
+        }
+    } else {
+        for (IdxT i = (IdxT)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+            const IdxT q = i / plane, r = i - q * plane, y = r / nx, x = r - y * nx;
+            const float l = exponent<MODE, P>(a.plan, voxel_coord<MODE>((uint32_t)x, a.nx), voxel_coord<MODE>((uint32_t)y, a.ny),
+                                              voxel_coord<MODE>(a.z0 + (uint32_t)q, a.nz), a.d);
+            store_voxel(a, base + i, l);
+        }
     }
 }
 

@@ -28,5 +28,6 @@ LYAP_DECLARE_MODE(host)
 cudaError_t launch_shade(int mode, const ShadeArgs &a, unsigned grid, cudaStream_t s);
 cudaError_t launch_scatter(const ScatterArgs &a, unsigned grid, cudaStream_t s);
 cudaError_t probe_peaks(double *ffma_ops, double *mufu_ops, double *clock_hz, int *sms);
+cudaError_t probe_ffma2(double *lane_ops);
 
 } // namespace lyap

@@ -87,6 +87,57 @@ __global__ void __launch_bounds__(256) probe_mufu_kernel(float *sink, float b, f
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
+__global__ void __launch_bounds__(256) probe_ffma2_kernel(float *sink, float b, float c, int iters)
+{
+    f32x2 x0 = pack2(threadIdx.x * 1e-3f, 1.f), x1 = pack2(2.f, 3.f), x2 = pack2(4.f, 5.f), x3 = pack2(6.f, 7.f);
+    f32x2 x4 = pack2(8.f, 9.f), x5 = pack2(10.f, 11.f), x6 = pack2(12.f, 13.f), x7 = pack2(14.f, 15.f);
+    const f32x2 bb = pack2(b, b), cc = pack2(c, c);
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = fma2(x0, bb, cc); x1 = fma2(x1, bb, cc); x2 = fma2(x2, bb, cc); x3 = fma2(x3, bb, cc);
+            x4 = fma2(x4, bb, cc); x5 = fma2(x5, bb, cc); x6 = fma2(x6, bb, cc); x7 = fma2(x7, bb, cc);
+        }
+    }
+    float lo, hi, s = 0.f;
+    unpack2(x0, lo, hi); s += lo + hi; unpack2(x1, lo, hi); s += lo + hi; unpack2(x2, lo, hi); s += lo + hi;
+    unpack2(x3, lo, hi); s += lo + hi; unpack2(x4, lo, hi); s += lo + hi; unpack2(x5, lo, hi); s += lo + hi;
+    unpack2(x6, lo, hi); s += lo + hi; unpack2(x7, lo, hi); s += lo + hi;
+    sink[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// Packed-FMA rate in scalar-lane-operations per second (two per packed lane-op).
+cudaError_t probe_ffma2(double *lane_ops)
+{
+    int dev = 0, n_sm = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    const int blocks = n_sm * 8, threads = 256, iters = 2048;
+    float *sink = nullptr;
+    if ((e = cudaMalloc(&sink, sizeof(float) * blocks * threads)) != cudaSuccess) return e;
+    cudaEvent_t ev0, ev1;
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        float ms = 0;
+        cudaEventRecord(ev0);
+        probe_ffma2_kernel<<<blocks, threads>>>(sink, 0.999f, 0.001f, iters);
+        cudaEventRecord(ev1);
+        if ((e = cudaEventSynchronize(ev1)) != cudaSuccess) break;
+        cudaEventElapsedTime(&ms, ev0, ev1);
+        const double ops = (double)blocks * threads * iters * 64.0 * 2.0 / (ms * 1e-3);
+        if (rep && ops > best) best = ops;
+    }
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    cudaFree(sink);
+    *lane_ops = best;
+    return e;
+}
+
 cudaError_t probe_peaks(double *ffma_ops, double *mufu_ops, double *clock_hz, int *sms)
 {
     int dev = 0, n_sm = 0;
