@@ -201,30 +201,43 @@ def main():
     d_lights = api.upload_lights(lights, dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
+    from lyapunov3d_b200 import dist as ld
+    peer = None
     if "w" in wl:
         w, h = wl["w"], wl["h"]
         rgba = torch.zeros((h, w, 4), dtype=torch.uint8, device=dev)
         pts = torch.zeros((h, w, 36), dtype=torch.uint8, device=dev)
-        gathered = [torch.zeros_like(rgba) for _ in range(world)] if (world > 1 and rank == 0) else None
+        frame_bytes = w * h * 4
+        if world > 1:
+            # rank 0 owns one RGBA slot per rank; every rank's kernel stores its frame straight
+            # into its slot over NVLink (CUDA IPC peer mapping): there is no gather step
+            peer = ld.PeerBuffer(frame_bytes * world)
 
         def step():
             pts.zero_()     # the frame contract: miss pixels shade a zeroed LyapPoint
-            _, _, ev = lp.render(cam, prm, seq, d_lights, n_lights, w, h, mode=args.mode, rgba=rgba, points=pts)
-            if world > 1:
-                dist.gather(rgba, gathered, dst=0)
+            if world == 1:
+                return lp.render(cam, prm, seq, d_lights, n_lights, w, h, mode=args.mode, rgba=rgba, points=pts)[2]
+            ev = torch.zeros(1, dtype=torch.int64, device=dev)
+            api.render_into(peer.ptr + rank * frame_bytes, pts.data_ptr(), cam, prm, seq, d_lights, n_lights, w, h,
+                            mode=args.mode, evals=ev)
+            torch.cuda.current_stream().synchronize()
+            dist.barrier()          # rank 0 may consume all frames of the step from here on
             return ev
         launches_per_step = 1
         units = w * h
     else:
         n = wl["n"]
-        z0, z1 = n * rank // world, n * (rank + 1) // world     # z-slab sharding: strong scaling
-        vol = torch.zeros((n, n, n), dtype=torch.float32, device=dev)
+        z0, z1 = ld.slab_range(n, rank, world)     # z-slab sharding: strong scaling
+        if world > 1:
+            peer = ld.PeerBuffer(n ** 3 * 4)       # the full volume lives on rank 0 only
+        else:
+            vol = torch.zeros((n, n, n), dtype=torch.float32, device=dev)
 
         def step():
-            lp.bake(prm, seq, n, z0=z0, z1=z1, mode=args.mode, out=vol)
-            if world > 1:
-                slabs = [vol[n * r // world:n * (r + 1) // world] for r in range(world)] if rank == 0 else None
-                dist.gather(vol[z0:z1], slabs, dst=0)
+            if world == 1:
+                lp.bake(prm, seq, n, mode=args.mode, out=vol)
+            else:
+                ld.bake_sharded_peer(peer, prm, seq, n, n, n, mode=args.mode)
             return torch.tensor([(z1 - z0) * n * n], device=dev)
         launches_per_step = 1
         units = n ** 3
@@ -301,6 +314,8 @@ def main():
                "ms_per_step": dt / args.steps * 1e3, "frames_per_s": args.steps * world / dt,
                "api": "lyap_render_host (C ABI, host buffers; alloc + H2D + kernel + D2H + sync per call)"}
 
+    if peer is not None:
+        peer.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -345,7 +360,8 @@ def main():
         "config": {"workload": wl["what"] + (", one frame per GPU per step" if "w" in wl else ", z-slabs across GPUs"),
                    "mode": args.mode, "sequence": wl["seq"], "settle": prm.settle, "accum": prm.accum,
                    "l2": "flushed between timed steps (256 MiB device write inside the timed region)",
-                   "gather": "NCCL gather of RGBA frames to rank 0 inside the timed region" if world > 1 else "none"},
+                   "gather": ("none needed: every rank's kernel stores its shard directly into rank 0's buffer over NVLink "
+                              "(CUDA IPC peer mapping); stream sync + barrier per step inside the timed region") if world > 1 else "none"},
         "frames_per_s": (args.steps * world / (ms * 1e-3)) if "w" in wl else None,
         "evaluations_per_step": total_evals / args.steps, "wall_ms": wall_ms,
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps * world,

@@ -136,6 +136,18 @@ int lyap_exponent_points(float *d_out, const float *d_xyz, uint64_t n, const lya
                          const int32_t *seq, int mode, void *stream);
 
 /* ----------------------------------------------------------------------------
+ * Peer memory for one-process-per-GPU sharding: rank 0 allocates the result buffer and
+ * exports a 64-byte CUDA IPC handle; the other ranks open it and pass the mapped pointer
+ * as d_exps / d_rgba / d_points above.  Their kernels then store their shard directly
+ * into rank 0's memory over NVLink -- there is no separate gather.
+ * ------------------------------------------------------------------------- */
+int lyap_peer_alloc(void **dptr, uint64_t bytes);              /* cudaMalloc + zero fill */
+int lyap_peer_free(void *dptr);
+int lyap_peer_export(void *dptr, unsigned char *handle64);     /* owner side */
+int lyap_peer_open(const unsigned char *handle64, void **dptr);/* other ranks */
+int lyap_peer_close(void *dptr);
+
+/* ----------------------------------------------------------------------------
  * Whole-call convenience with HOST buffers (allocations, copies and the final
  * synchronise happen inside; this is the end-to-end path bench.py times).
  * ------------------------------------------------------------------------- */

@@ -69,6 +69,11 @@ def lib():
     L.lyap_write_raw.argtypes = [C.c_char_p, vp, u64]
     L.lyap_format_filename.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_ulong, u32, u32, C.c_char_p, vp, vp]
     L.lyap_probe_peaks.argtypes = [vp, vp, vp, vp]
+    L.lyap_peer_alloc.argtypes = [C.POINTER(vp), u64]
+    L.lyap_peer_free.argtypes = [vp]
+    L.lyap_peer_export.argtypes = [vp, vp]
+    L.lyap_peer_open.argtypes = [vp, C.POINTER(vp)]
+    L.lyap_peer_close.argtypes = [vp]
     L.lyap_probe_ffma2.argtypes = [vp]
     _lib = L
     return L
@@ -246,6 +251,42 @@ def exponent_points(xyz, prm, seq, mode="exact"):
     _check(lib().lyap_exponent_points(out.data_ptr(), xyz.data_ptr(), xyz.shape[0], C.byref(prm), seq.ctypes.data,
                                       _mode(mode), _stream_ptr(torch)), "lyap_exponent_points")
     return out
+
+
+# ---------------------------------------------------------------- raw pointers
+class DevicePointer:
+    """A device pointer that is not owned by torch (a peer-mapped buffer, say), exposed through
+    __cuda_array_interface__ so that torch.as_tensor() can view it and, duck-typed with
+    data_ptr(), so that render()/bake() accept it as an output buffer."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.ptr, self.shape, self.typestr = int(ptr), tuple(shape), typestr
+        self.__cuda_array_interface__ = {"shape": self.shape, "typestr": typestr, "data": (self.ptr, False), "version": 2}
+
+    def data_ptr(self):
+        return self.ptr
+
+    def tensor(self):
+        return _torch().as_tensor(self, device="cuda")
+
+
+def render_into(d_rgba, d_points, cam, prm, seq, d_lights, num_lights, width, height, mode="exact", tile=8, rank=0, world=1,
+                evals=None):
+    """lyap_render_tiles on raw device pointers (ints): in-place (non-compact) tile render."""
+    torch = _torch()
+    seq = np.ascontiguousarray(seq, np.int32)
+    ev_ptr = C.c_void_p(evals.data_ptr()) if evals is not None else None
+    _check(lib().lyap_render_tiles(int(d_rgba), int(d_points), C.byref(cam), C.byref(prm), seq.ctypes.data, d_lights.data_ptr(),
+                                   num_lights, width, height, tile, rank, world, 0, _mode(mode), ev_ptr, _stream_ptr(torch)),
+           "lyap_render_tiles")
+
+
+def bake_ptr(d_exps, f16, prm, seq, nx, ny, nz, z0, z1, mode="fast"):
+    """lyap_bake on a raw device pointer to the FULL volume."""
+    torch = _torch()
+    seq = np.ascontiguousarray(seq, np.int32)
+    _check(lib().lyap_bake(int(d_exps), F16 if f16 else F32, C.byref(prm), seq.ctypes.data, nx, ny, nz, z0, z1, _mode(mode),
+                           _stream_ptr(torch)), "lyap_bake")
 
 
 # ------------------------------------------------------------- host-buffer path

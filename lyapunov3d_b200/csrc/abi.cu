@@ -400,6 +400,42 @@ int lyap_bake_host(void *h_exps, int dtype, const lyap_params *prm, const int32_
     return (int)e;
 }
 
+// ------------------------------------------------------------------ peer memory
+// One process per GPU: rank 0 allocates the result buffer, exports a CUDA IPC handle, the
+// other ranks map it and hand the mapped pointer to lyap_bake / lyap_render_tiles, whose
+// kernels then store their shard straight into rank 0's HBM over NVLink/NVSwitch.  No
+// gather step exists: the "collective" is the kernels' own stores.
+int lyap_peer_alloc(void **dptr, uint64_t bytes)
+{
+    if (!dptr || !bytes) return LYAP_ERR_BAD_ARGUMENT;
+    cudaError_t e = cudaMalloc(dptr, bytes);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaMemset(*dptr, 0, bytes);
+}
+
+int lyap_peer_free(void *dptr) { return (int)cudaFree(dptr); }
+
+int lyap_peer_export(void *dptr, unsigned char *handle64)
+{
+    if (!dptr || !handle64) return LYAP_ERR_BAD_ARGUMENT;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, dptr);
+    if (e != cudaSuccess) return (int)e;
+    memcpy(handle64, &h, 64);
+    return LYAP_OK;
+}
+
+int lyap_peer_open(const unsigned char *handle64, void **dptr)
+{
+    if (!dptr || !handle64) return LYAP_ERR_BAD_ARGUMENT;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    return (int)cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess);
+}
+
+int lyap_peer_close(void *dptr) { return (int)cudaIpcCloseMemHandle(dptr); }
+
 int lyap_probe_ffma2(double *packed_ffma_lane_ops_per_s)
 {
     double v = 0;

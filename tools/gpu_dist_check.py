@@ -53,6 +53,25 @@ vol = ld.bake_sharded(prm, seq, 48, 40, 36 + world - 1, mode="fast")
 if rank == 0:
     v1 = lp.bake(prm, seq, 48, 40, 36 + world - 1, mode="fast")
     assert torch.equal(vol.view(torch.int32), v1.view(torch.int32))
+# ---- peer-memory variants: kernels store straight into rank 0's buffers, no gather
+dev = torch.device("cuda", local)
+d_lights = api.upload_lights(lights, dev)
+p_rgba, p_pts = ld.PeerBuffer(w * h * 4), ld.PeerBuffer(w * h * 36)
+ev = torch.zeros(1, dtype=torch.int64, device=dev)
+ld.render_frame_sharded_peer(p_rgba, p_pts, c, prm, seq, d_lights, n, w, h, mode="exact", evals=ev)
+if rank == 0:
+    r1, p1, e1 = lp.render(c, prm, seq, lights, n, w, h, mode="exact")
+    assert torch.equal(p_rgba.view((h, w, 4), "|u1").tensor(), r1) and torch.equal(p_pts.view((h, w, 36), "|u1").tensor(), p1)
+p_rgba.close(); p_pts.close()
+nzp = 36 + world - 1
+p_vol = ld.PeerBuffer(48 * 40 * nzp * 4)
+ld.bake_sharded_peer(p_vol, prm, seq, 48, 40, nzp, mode="fast")
+if rank == 0:
+    v1 = lp.bake(prm, seq, 48, 40, nzp, mode="fast")
+    assert torch.equal(p_vol.view((nzp, 40, 48), "<f4").tensor().view(torch.int32), v1.view(torch.int32))
+    print("peer-memory sharding ok on", world, "GPUs", flush=True)
+p_vol.close()
+
 frames = ld.render_animation_sharded(2 * world + 1, 64, 36, prm, cam, seq, lights, n, mode="exact")
 if rank == 0:
     for f, fr in enumerate(frames):
@@ -68,6 +87,11 @@ if timing:
     for mode in ("fast", "exact"):
         _, t = timed(lambda: ld.bake_sharded(prm, seq, 512, mode=mode))
         out[f"bake512_{mode}"] = {"s": t, "giter_s": 512 ** 3 * iters / t / 1e9}
+    p_vol = ld.PeerBuffer(512 ** 3 * 4)
+    for mode in ("fast", "exact"):
+        _, t = timed(lambda: ld.bake_sharded_peer(p_vol, prm, seq, 512, 512, 512, mode=mode), reps=3)
+        out[f"bake512_{mode}_peer"] = {"s": t, "giter_s": 512 ** 3 * iters / t / 1e9}
+    p_vol.close()
     # config 2 frame tile-sharded (strong scaling of one 1080p frame)
     c2 = clone(cam)
     lp.scene_cam_recalculate(c2, 1920, 1080, 1)
@@ -90,6 +114,15 @@ if timing:
         if rank == 0 and mode == "exact":
             os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
             api.write_png(os.path.join(ROOT, "gpurun_out", "frame4k_long_exact.png"), rgba.cpu().numpy())
+    # the same two frames through peer memory (no gather, no scatter)
+    for name, (cc, pp, ss, ww, hh, per) in {"frame1080_tiles": (c2, prm, seq, 1920, 1080, iters), "frame4k_long": (c3, p3, s3, 3840, 2160, 4104)}.items():
+        p_rgba, p_pts = ld.PeerBuffer(ww * hh * 4), ld.PeerBuffer(ww * hh * 36)
+        for mode in ("exact", "fast"):
+            ev = torch.zeros(1, dtype=torch.int64, device=dev)
+            _, t = timed(lambda: ld.render_frame_sharded_peer(p_rgba, p_pts, cc, pp, ss, d_lights, n, ww, hh, mode=mode, evals=ev), reps=1)
+            dist.all_reduce(ev)
+            out[f"{name}_{mode}_peer"] = {"s": t, "giter_s": int(ev.item()) * per / t / 1e9, "fps": 1 / t}
+        p_rgba.close(); p_pts.close()
     # config 5: 120-frame 1080p orbit, frames dealt to ranks
     n_frames = 120 if world >= 4 else 8 * world
     count = [0]
