@@ -384,3 +384,83 @@ def test_multi_gpu_shards_equal_single_gpu():
                         "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "gpu_dist_check.py")],
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "dist correctness ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+# ------------------------------------------------------------------ edge cases
+def test_edge_cases_against_oracle(oracle, scene):
+    """Degenerate sizes and parameters the reference accepts: 1-pixel frames, no lights, all 16
+    lights, a camera that misses everything, one accumulate step, no settle steps."""
+    prm, cam, lights, n, seq = scene
+
+    def both(c, p, sq, L, nl, w, h):
+        want_rgba, want_pts, _ = oracle.render(c, p, sq, L, nl, w, h)
+        rgba, pts, _ = lp.render(c, p, sq, L, nl, w, h, mode="host")
+        assert point_rows_equal(points_np(pts), want_pts).all()
+        # pixels go through powf, which is CUDA's in HOST mode (not glibc's): allow the stated 2/255
+        assert frac_within(rgba.cpu().numpy(), want_rgba, PIXEL_TOL) >= PIXEL_FRAC
+
+    for (w, h) in ((1, 1), (1, 7), (9, 1), (17, 3)):
+        c = clone(cam)
+        lp.scene_cam_recalculate(c, w, h, 1)
+        both(c, prm, seq, lights, n, w, h)
+    c = clone(cam)
+    lp.scene_cam_recalculate(c, 24, 16, 1)
+    both(c, prm, seq, lights, 0, 24, 16)                       # no lights: black, alpha 0
+    many = clone(lights)
+    for k in range(1, 16):
+        many[k] = many[0]
+        many[k].C.x += 0.3 * k
+        many[k].diffuseColor.g = 0.05 * k
+    lp.scene_lights_recalculate(many, 16)
+    both(c, prm, seq, many, 16, 24, 16)                        # MAX_LIGHTS
+    away = clone(c)
+    away.C.x, away.C.y, away.C.z = 40.0, 41.0, 42.0            # looking at the cube from far away: mostly misses
+    both(away, prm, seq, lights, n, 24, 16)
+    p1 = clone(prm)
+    p1.settle, p1.accum = 0, 1
+    both(c, p1, seq, lights, n, 16, 12)
+    p2 = clone(prm)
+    p2.depth, p2.refine, p2.nearMultiplier = 64.0, 4.0, 8.0
+    both(c, p2, lp.scene_convert_sequence("AABAB"), lights, n, 16, 12)
+
+
+def test_render_bad_arguments(scene):
+    prm, cam, lights, n, seq = scene
+    with pytest.raises(lp.LyapError):
+        lp.render(cam, prm, np.array([4, -1], np.int32), lights, n, 8, 8)
+    with pytest.raises(lp.LyapError):
+        lp.render(cam, prm, seq, lights, 17, 8, 8)
+    with pytest.raises(lp.LyapError):
+        lp.render(cam, prm, seq, lights, n, 8, 8, mode=5)
+    with pytest.raises(lp.LyapError):
+        lp.render(cam, prm, seq, lights, n, 8, 8, tile=8, rank=3, world=2)
+
+
+def test_headless_apps(tmp_path, scene):
+    """The two re-hosted programs (csrc/apps): same bytes as the library calls they wrap."""
+    import os
+    import subprocess
+    prm, cam, lights, n, seq = scene
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    bindir = os.path.join(root, "lyapunov3d_b200", "bin")
+    raw = tmp_path / "exps.raw"
+    r = subprocess.run([os.path.join(bindir, "lyap_calculate"), "-n", "24", "-mode", "exact", "-o", str(raw)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    vol = np.fromfile(raw, np.float32).reshape(24, 24, 24)
+    assert same_floats(vol, lp.bake(prm, seq, 24, mode="exact").cpu().numpy())
+    r = subprocess.run([os.path.join(bindir, "lyap_render"), "-w", "48", "-h", "32", "-mode", "host", "-ppm", "-png", "-points", "-dir", str(tmp_path)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    c = clone(cam)
+    lp.scene_cam_recalculate(c, 48, 32, 1)
+    rgba, pts, _ = lp.render(c, prm, seq, lights, n, 48, 32, mode="host")
+    files = sorted(os.listdir(tmp_path))
+    ppm = [f for f in files if f.endswith(".ppm")][0]
+    pts_file = [f for f in files if f.startswith("Points_")][0]
+    assert ppm.startswith("Render_") and "_48x32_BCABA_cx=" in ppm and "_time=0h00m" in ppm
+    vals = np.array(open(tmp_path / ppm).read().split()[4:], dtype=np.int64).reshape(32, 48, 3)
+    assert np.array_equal(vals, rgba.cpu().numpy()[..., :3])
+    assert open(tmp_path / pts_file, "rb").read() == pts.cpu().numpy().tobytes()
+    from PIL import Image
+    png = [f for f in files if f.endswith(".png")][0]
+    assert np.array_equal(np.asarray(Image.open(tmp_path / png).convert("RGB")), rgba.cpu().numpy()[..., :3])
