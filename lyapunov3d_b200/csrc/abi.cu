@@ -67,6 +67,7 @@ int build_plan(SeqPlan &sp, const int32_t *seq, uint32_t settle, uint32_t accum)
     const uint32_t L = P > 0 ? (uint32_t)P : per;
     memset(&sp, 0, sizeof sp);
     sp.len = L;
+    sp.fold_bias = (uint32_t)(127 + Accum<kFast>::kBias) << 23;
     sp.settle = settle;
     sp.accum = accum;
     for (uint32_t i = 0; i < L; ++i) sp.sym[i] = (uint8_t)seq[i % per];
@@ -293,6 +294,8 @@ int lyap_bake(void *d_exps, int dtype, const lyap_params *prm, const int32_t *se
         const uint32_t zb = (z1 - za > max_planes) ? za + max_planes : z1;
         a.z0 = za;
         a.z1 = zb;
+        a.queue = sc->counters + (sc->next.fetch_add(1) % kCounterRing);
+        if ((e = cudaMemsetAsync(a.queue, 0, sizeof(unsigned long long), s)) != cudaSuccess) break;
         const unsigned long long total = plane * (zb - za);
         const unsigned long long per_thread = (mode == LYAP_MODE_FAST) ? 2 : 1;
         unsigned long long grid = (unsigned long long)sc->sm_count * per_sm;

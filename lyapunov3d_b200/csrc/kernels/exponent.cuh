@@ -43,6 +43,8 @@ struct SeqPlan {
     uint32_t accum_periods;   // accum / len
     uint32_t accum_tail;      // accum % len
     uint32_t cnt[4];          // how often each symbol occurs among the accum steps
+    uint32_t fold_bias;       // float bits of 2^kBias; a run-time value so that each fold's
+                              // (bits & mantissa) | bias stays ONE three-input LOP3
     uint8_t rot[kMaxPeriodRegs];  // sym rotated left by settle_head: the order both period loops see
     uint8_t sym[kMaxSeq];         // the period as written
 };
@@ -127,13 +129,14 @@ struct Accum<kFast> {
         float q = __fmaf_rn(-2.0f, v, 1.0f);
         prod = __fmul_rn(prod, fabsf(q));
     }
+    int bias_bits;   // = (127 + kBias) << 23, from SeqPlan::fold_bias
     __device__ __forceinline__ void renorm()
     {
         int bits = __float_as_int(prod);
         int e = bits >> 23;  // prod >= 0: no sign bit
         esum += e - (127 + kBias);
         emin = min(emin, e);
-        prod = __int_as_float((bits & 0x007fffff) | ((127 + kBias) << 23));
+        prod = __int_as_float((bits & 0x007fffff) | bias_bits);
     }
     __device__ __forceinline__ float finish(const SeqPlan &sp, float x, float y, float z, float d, float v)
     {
@@ -163,6 +166,7 @@ __device__ __forceinline__ float exponent(const SeqPlan &sp, float x, float y, f
     float v = 0.5f;
     Accum<MODE> acc;
     acc.init();
+    if constexpr (MODE == kFast) acc.bias_bits = (int)sp.fold_bias;
     float v_settled;
 
     if constexpr (P > 0) {
@@ -265,9 +269,10 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
 struct AccumFast2 {
     static constexpr int kBias = Accum<kFast>::kBias;
     f32x2 prod;
-    int esum0, esum1, emin0, emin1;
-    __device__ __forceinline__ void init()
+    int esum0, esum1, emin0, emin1, bias_bits;
+    __device__ __forceinline__ void init(uint32_t fold_bias)
     {
+        bias_bits = (int)fold_bias;
         const float b = __int_as_float((127 + kBias) << 23);
         prod = pack2(b, b);
         esum0 = esum1 = 0;
@@ -283,14 +288,13 @@ struct AccumFast2 {
     {
         float a, b;
         unpack2(prod, a, b);
-        const int ba = __float_as_int(a) & 0x7fffffff, bb = __float_as_int(b) & 0x7fffffff;
-        const int ea = ba >> 23, eb = bb >> 23;
+        const int ba = __float_as_int(a), bb = __float_as_int(b);
+        const int ea = (ba >> 23) & 0xff, eb = (bb >> 23) & 0xff;   // the sign of prod is not tracked: drop it
         esum0 += ea - (127 + kBias);
         esum1 += eb - (127 + kBias);
         emin0 = min(emin0, ea);
         emin1 = min(emin1, eb);
-        prod = pack2(__int_as_float((ba & 0x007fffff) | ((127 + kBias) << 23)),
-                     __int_as_float((bb & 0x007fffff) | ((127 + kBias) << 23)));
+        prod = pack2(__int_as_float((ba & 0x007fffff) | bias_bits), __int_as_float((bb & 0x007fffff) | bias_bits));
     }
 };
 
@@ -316,7 +320,7 @@ __device__ __forceinline__ void exponent_fast2(const SeqPlan &sp, float xa, floa
     const f32x2 two = pack2(2.0f, 2.0f), one = pack2(1.0f, 1.0f);
     f32x2 w = pack2(-0.5f, -0.5f);
     AccumFast2 acc;
-    acc.init();
+    acc.init(sp.fold_bias);
     float vsa, vsb;
     auto rpair = [&](uint32_t s) { return pack2(sel4(s, xa, ya, za, d), sel4(s, xb, yb, zb, d)); };
     auto settle_step = [&](f32x2 r) {

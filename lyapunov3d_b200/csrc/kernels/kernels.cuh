@@ -24,6 +24,7 @@ struct BakeArgs {
     void *out;       // full volume
     int f16;         // 0: float, 1: __half
     uint32_t nx, ny, nz, z0, z1;
+    unsigned long long *queue;   // next unclaimed work item of this launch (zeroed before launch)
 };
 
 template <int MODE>
@@ -44,6 +45,11 @@ __device__ __forceinline__ void store_voxel(const BakeArgs &a, uint64_t idx, flo
 }
 
 // Index arithmetic is 32-bit: lyap_bake() splits a slab into launches of < 2^31 voxels.
+//
+// Work is handed out dynamically, 32 consecutive items per warp per grab (one atomicAdd per
+// ~10^4 cycles of work).  With a static grid-stride partition the warp scheduler's fixed
+// priorities let some warps finish at half time and the pipes starve while the stragglers
+// finish alone (ncu: 6.3 of 10 resident warps active on average, FMA pipe 83 % busy).
 template <int MODE, int P>
 __global__ void __launch_bounds__(256) bake_kernel(const __grid_constant__ BakeArgs a)
 {
@@ -52,14 +58,22 @@ __global__ void __launch_bounds__(256) bake_kernel(const __grid_constant__ BakeA
     const IdxT nx = a.nx;
     const IdxT plane = (IdxT)a.nx * (IdxT)a.ny;
     const IdxT total = plane * (IdxT)(a.z1 - a.z0);
-    const IdxT stride = (IdxT)gridDim.x * blockDim.x;
     const uint64_t base = (uint64_t)a.z0 * a.nx * a.ny;
-    if constexpr (MODE == kFast) {
-        // two x-adjacent voxels per lane through the packed evaluator: a warp covers 64
-        // consecutive voxels and stores 256 contiguous bytes (FP32)
-        const IdxT pairs = total / 2 + (total & 1);
-        for (IdxT k = (IdxT)blockIdx.x * blockDim.x + threadIdx.x; k < pairs; k += stride) {
-            const IdxT i0 = 2 * k, i1 = (2 * k + 1 < total) ? 2 * k + 1 : 2 * k;
+    const unsigned lane = threadIdx.x & 31;
+    const IdxT items = (MODE == kFast) ? total / 2 + (total & 1) : total;   // fast mode: voxel pairs
+    for (;;) {
+        unsigned long long first = 0;
+        if (lane == 0) first = atomicAdd(a.queue, 32ull);
+        first = __shfl_sync(0xffffffffu, first, 0);
+        if (first >= items) break;
+        const IdxT k = (IdxT)first + lane;
+        // lanes past the end of the slab evaluate a duplicate of the last item and skip the store
+        const bool live = k < items;
+        const IdxT kk = live ? k : items - 1;
+        if constexpr (MODE == kFast) {
+            // two x-adjacent voxels per lane through the packed evaluator: a warp covers 64
+            // consecutive voxels and stores 256 contiguous bytes (FP32)
+            const IdxT i0 = 2 * kk, i1 = (2 * kk + 1 < total) ? 2 * kk + 1 : 2 * kk;
             const IdxT q0 = i0 / plane, r0 = i0 - q0 * plane, y0 = r0 / nx, x0 = r0 - y0 * nx;
             IdxT q1 = q0, y1 = y0, x1 = x0;
             if (i1 != i0) {
@@ -70,22 +84,22 @@ __global__ void __launch_bounds__(256) bake_kernel(const __grid_constant__ BakeA
             exponent_fast2<P>(a.plan, voxel_coord<MODE>((uint32_t)x0, a.nx), voxel_coord<MODE>((uint32_t)y0, a.ny),
                               voxel_coord<MODE>(a.z0 + (uint32_t)q0, a.nz), voxel_coord<MODE>((uint32_t)x1, a.nx),
                               voxel_coord<MODE>((uint32_t)y1, a.ny), voxel_coord<MODE>(a.z0 + (uint32_t)q1, a.nz), a.d, l0, l1);
-            const uint64_t o0 = base + i0;
-            if (!a.f16 && i1 != i0 && (o0 & 1) == 0) {
-                reinterpret_cast<float2 *>(a.out)[o0 >> 1] = make_float2(l0, l1);
-            } else if (a.f16 && i1 != i0 && (o0 & 1) == 0) {
-                reinterpret_cast<__half2 *>(a.out)[o0 >> 1] = __floats2half2_rn(l0, l1);
-            } else {
-                store_voxel(a, o0, l0);
-                if (i1 != i0) store_voxel(a, o0 + 1, l1);
+            if (live) {
+                const uint64_t o0 = base + i0;
+                if (!a.f16 && i1 != i0 && (o0 & 1) == 0) {
+                    reinterpret_cast<float2 *>(a.out)[o0 >> 1] = make_float2(l0, l1);
+                } else if (a.f16 && i1 != i0 && (o0 & 1) == 0) {
+                    reinterpret_cast<__half2 *>(a.out)[o0 >> 1] = __floats2half2_rn(l0, l1);
+                } else {
+                    store_voxel(a, o0, l0);
+                    if (i1 != i0) store_voxel(a, o0 + 1, l1);
+                }
             }
-        }
-    } else {
-        for (IdxT i = (IdxT)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-            const IdxT q = i / plane, r = i - q * plane, y = r / nx, x = r - y * nx;
+        } else {
+            const IdxT q = kk / plane, r = kk - q * plane, y = r / nx, x = r - y * nx;
             const float l = exponent<MODE, P>(a.plan, voxel_coord<MODE>((uint32_t)x, a.nx), voxel_coord<MODE>((uint32_t)y, a.ny),
                                               voxel_coord<MODE>(a.z0 + (uint32_t)q, a.nz), a.d);
-            store_voxel(a, base + i, l);
+            if (live) store_voxel(a, base + kk, l);
         }
     }
 }
@@ -218,6 +232,74 @@ __global__ void __launch_bounds__(kRenderThreads) render_kernel(const __grid_con
                 }
                 finish_pixel<A>(a, st, ev == kHit);
                 st.phase = kNeedRay;
+            }
+        }
+    }
+
+    if (a.evals) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) evals += __shfl_xor_sync(full, evals, o);
+        if (lane == 0) atomicAdd(a.evals, evals);
+    }
+}
+
+// Fast mode: TWO rays per lane, evaluated together by the packed (f32x2) exponent.  The
+// single-ray fast kernel is issue-bound (92 % of issue slots busy for 75 % FMA-pipe use,
+// profiles/r01_render_fast_1080p.md); FFMA2/FMUL2 carry two rays' steps in one issue slot.
+template <int P>
+__global__ void __launch_bounds__(kRenderThreads, 3) render_fast2_kernel(const __grid_constant__ RenderArgs a)
+{
+    using A = ArithDev;
+    const unsigned full = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31;
+    RayState st[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        st[j].phase = kNeedRay;
+        st[j].sx = st[j].sy = st[j].sz = 2.0f;
+    }
+    bool drained = false;
+    unsigned long long evals = 0;
+
+    for (;;) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            for (;;) {
+                const bool need = st[j].phase == kNeedRay;
+                const unsigned m = __ballot_sync(full, need);
+                if (m == 0 || drained) break;
+                const int leader = __ffs(m) - 1;
+                const unsigned n_need = __popc(m);
+                unsigned long long base = 0;
+                if ((int)lane == leader) base = atomicAdd(a.queue, (unsigned long long)n_need);
+                base = __shfl_sync(full, base, leader);
+                if (need) {
+                    const unsigned long long k = base + __popc(m & ((1u << lane) - 1u));
+                    uint32_t px, py;
+                    if (k < a.n_items && item_to_pixel(a, k, px, py)) {
+                        st[j].out = a.compact ? (uint32_t)k : px + py * a.width;
+                        if (!ray_begin<A>(st[j], px, py, a.cam, a.prm)) finish_pixel<A>(a, st[j], false);
+                    }
+                }
+                if (base + n_need >= a.n_items) drained = true;
+            }
+        }
+        const bool act0 = st[0].phase != kNeedRay, act1 = st[1].phase != kNeedRay;
+        if (__ballot_sync(full, act0 || act1) == 0) break;
+
+        float l[2];
+        exponent_fast2<P>(a.plan, st[0].sx, st[0].sy, st[0].sz, st[1].sx, st[1].sy, st[1].sz, a.prm.d, l[0], l[1]);
+
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            if (st[j].phase != kNeedRay) {
+                ++evals;
+                const RayEvent ev = ray_advance<A>(st[j], l[j], a.prm);
+                if (ev != kContinue) {
+                    if (ev == kHit) normalize3<A>(st[j].Nx, st[j].Ny, st[j].Nz);
+                    finish_pixel<A>(a, st[j], ev == kHit);
+                    st[j].phase = kNeedRay;
+                }
             }
         }
     }

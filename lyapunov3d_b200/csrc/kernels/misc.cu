@@ -1,5 +1,6 @@
 // misc.cu -- shade-only pass, tile scatter, and the roofline probe kernels.
 #include <cstdio>
+#include <cstdlib>
 
 #include "launch.hpp"
 
@@ -87,6 +88,36 @@ __global__ void __launch_bounds__(256) probe_mufu_kernel(float *sink, float b, f
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
+template <int VARIANT>
+__global__ void __launch_bounds__(256) probe_packed_kernel(float *sink, float b, float c, int iters)
+{
+    f32x2 x0 = pack2(threadIdx.x * 1e-3f, 1.f), x1 = pack2(2.f, 3.f), x2 = pack2(4.f, 5.f), x3 = pack2(6.f, 7.f);
+    f32x2 x4 = pack2(8.f, 9.f), x5 = pack2(10.f, 11.f), x6 = pack2(12.f, 13.f), x7 = pack2(14.f, 15.f);
+    const f32x2 bb = pack2(b, b), cc = pack2(c, c), two = pack2(2.f, 2.f), one = pack2(1.f, 1.f);
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if constexpr (VARIANT == 1) {
+                x0 = mul2(x0, bb); x1 = mul2(x1, bb); x2 = mul2(x2, bb); x3 = mul2(x3, bb);
+                x4 = mul2(x4, bb); x5 = mul2(x5, bb); x6 = mul2(x6, bb); x7 = mul2(x7, bb);
+            } else {
+                // four independent (w, prod) pairs doing the fast exponent step: 2 mul2 + 2 fma2 each
+                f32x2 p;
+                p = mul2(bb, x0); x0 = fma2(p, x0, p); x1 = mul2(x1, fma2(two, x0, one));
+                p = mul2(cc, x2); x2 = fma2(p, x2, p); x3 = mul2(x3, fma2(two, x2, one));
+                p = mul2(bb, x4); x4 = fma2(p, x4, p); x5 = mul2(x5, fma2(two, x4, one));
+                p = mul2(cc, x6); x6 = fma2(p, x6, p); x7 = mul2(x7, fma2(two, x6, one));
+            }
+        }
+    }
+    float lo, hi, s = 0.f;
+    unpack2(x0, lo, hi); s += lo + hi; unpack2(x1, lo, hi); s += lo + hi; unpack2(x2, lo, hi); s += lo + hi;
+    unpack2(x3, lo, hi); s += lo + hi; unpack2(x4, lo, hi); s += lo + hi; unpack2(x5, lo, hi); s += lo + hi;
+    unpack2(x6, lo, hi); s += lo + hi; unpack2(x7, lo, hi); s += lo + hi;
+    sink[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 __global__ void __launch_bounds__(256) probe_ffma2_kernel(float *sink, float b, float c, int iters)
 {
     f32x2 x0 = pack2(threadIdx.x * 1e-3f, 1.f), x1 = pack2(2.f, 3.f), x2 = pack2(4.f, 5.f), x3 = pack2(6.f, 7.f);
@@ -130,6 +161,20 @@ cudaError_t probe_ffma2(double *lane_ops)
         cudaEventElapsedTime(&ms, ev0, ev1);
         const double ops = (double)blocks * threads * iters * 64.0 * 2.0 / (ms * 1e-3);
         if (rep && ops > best) best = ops;
+        if (rep == 3 && getenv("LYAP_PROBE_VERBOSE")) {
+            cudaEventRecord(ev0);
+            probe_packed_kernel<1><<<blocks, threads>>>(sink, 0.999f, 0.5f, iters);
+            cudaEventRecord(ev1);
+            cudaEventSynchronize(ev1);
+            cudaEventElapsedTime(&ms, ev0, ev1);
+            printf("probe mul2 chains: %.2f T lane-ops/s\n", (double)blocks * threads * iters * 64.0 * 2.0 / (ms * 1e-3) / 1e12);
+            cudaEventRecord(ev0);
+            probe_packed_kernel<2><<<blocks, threads>>>(sink, 3.7f, 3.2f, iters);
+            cudaEventRecord(ev1);
+            cudaEventSynchronize(ev1);
+            cudaEventElapsedTime(&ms, ev0, ev1);
+            printf("probe fast-step mix (2 mul2 + 2 fma2, 4 chains): %.2f T lane-ops/s\n", (double)blocks * threads * iters * 8 * 16.0 * 2.0 / (ms * 1e-3) / 1e12);
+        }
     }
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);

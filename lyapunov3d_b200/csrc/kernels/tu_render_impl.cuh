@@ -3,13 +3,23 @@
 
 namespace lyap {
 
+// fast mode renders two rays per lane through the packed evaluator
+template <int MODE, int P>
+struct RenderKernelOf {
+    static constexpr void (*fn)(RenderArgs) = render_kernel<MODE, P>;
+};
+template <int P>
+struct RenderKernelOf<kFast, P> {
+    static constexpr void (*fn)(RenderArgs) = render_fast2_kernel<P>;
+};
+#define LYAP_RENDER_KERNEL(p) RenderKernelOf<LYAP_TU_MODE, p>::fn
 #define LYAP_CAT2(a, b) a##b
 #define LYAP_CAT(a, b) LYAP_CAT2(a, b)
 
 cudaError_t LYAP_CAT(launch_render_, LYAP_TU_NAME)(int P, const RenderArgs &a, unsigned grid, cudaStream_t s)
 {
     switch (P) {
-#define X(p) case p: render_kernel<LYAP_TU_MODE, p><<<grid, kRenderThreads, 0, s>>>(a); break;
+#define X(p) case p: LYAP_RENDER_KERNEL(p)<<<grid, kRenderThreads, 0, s>>>(a); break;
         LYAP_PERIODS(X)
 #undef X
     default: return cudaErrorInvalidValue;
@@ -21,7 +31,7 @@ int LYAP_CAT(render_blocks_per_sm_, LYAP_TU_NAME)(int P)
 {
     int n = 0;
     switch (P) {
-#define X(p) case p: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, render_kernel<LYAP_TU_MODE, p>, kRenderThreads, 0); break;
+#define X(p) case p: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, LYAP_RENDER_KERNEL(p), kRenderThreads, 0); break;
         LYAP_PERIODS(X)
 #undef X
     default: break;
