@@ -71,6 +71,16 @@ int build_plan(SeqPlan &sp, const int32_t *seq, uint32_t settle, uint32_t accum)
     sp.settle = settle;
     sp.accum = accum;
     for (uint32_t i = 0; i < L; ++i) sp.sym[i] = (uint8_t)seq[i % per];
+    // run-length form of the same period (runs split at 255; a run never wraps around the period end)
+    sp.n_runs = 0;
+    for (uint32_t i = 0; i < L;) {
+        uint32_t j = i;
+        while (j < L && sp.sym[j] == sp.sym[i] && j - i < 255) ++j;
+        sp.runs[2 * sp.n_runs] = sp.sym[i];
+        sp.runs[2 * sp.n_runs + 1] = (uint8_t)(j - i);
+        ++sp.n_runs;
+        i = j;
+    }
     sp.settle_head = settle % L;
     sp.settle_periods = settle / L;
     sp.accum_periods = accum / L;

@@ -45,9 +45,45 @@ struct SeqPlan {
     uint32_t cnt[4];          // how often each symbol occurs among the accum steps
     uint32_t fold_bias;       // float bits of 2^kBias; a run-time value so that each fold's
                               // (bits & mantissa) | bias stays ONE three-input LOP3
+    uint32_t n_runs;          // run-length form of the period (generic path): number of (symbol, length) pairs
     uint8_t rot[kMaxPeriodRegs];  // sym rotated left by settle_head: the order both period loops see
-    uint8_t sym[kMaxSeq];         // the period as written
+    uint8_t sym[kMaxSeq];         // the period as written (register-table path)
+    uint8_t runs[2 * kMaxSeq];    // (symbol, length <= 255) pairs covering one period (generic path)
 };
+
+// Cursor over the run-length encoded period: which run, how far into it.
+struct RunCursor {
+    uint32_t run, off;
+};
+
+// Take `count` steps of the sequence from the cursor, calling step(r) once per step with the
+// multiplier of the current run, fold() after every 8 steps and at the end of every run segment.
+// Everything here is warp-uniform; the inner 8-step loop is unrolled with r in a register.
+template <class Sel, class Step, class Fold>
+__device__ __forceinline__ void run_steps(const SeqPlan &sp, RunCursor &cur, uint32_t count, Sel sel, Step step, Fold fold)
+{
+    while (count) {
+        const uint32_t sym = sp.runs[2 * cur.run], len = sp.runs[2 * cur.run + 1];
+        const uint32_t n = min(len - cur.off, count);
+        const auto r = sel(sym);
+        uint32_t i = 0;
+#pragma unroll 1
+        for (; i + 8 <= n; i += 8) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) step(r);
+            fold();
+        }
+#pragma unroll 1
+        for (; i < n; ++i) step(r);
+        fold();
+        count -= n;
+        cur.off += n;
+        if (cur.off == len) {
+            cur.off = 0;
+            cur.run = (cur.run + 1 == sp.n_runs) ? 0 : cur.run + 1;
+        }
+    }
+}
 
 __device__ __forceinline__ float sel4(uint32_t s, float x, float y, float z, float d)
 {
@@ -208,19 +244,11 @@ __device__ __forceinline__ float exponent(const SeqPlan &sp, float x, float y, f
             if ((n & 7) == 7) acc.renorm();
         }
     } else {
-        uint32_t pos = 0;
-#pragma unroll 1
-        for (uint32_t n = 0; n < sp.settle; n++) {
-            logistic_step<MODE>(sel4(sp.sym[pos], x, y, z, d), v);
-            pos = (pos + 1 == sp.len) ? 0 : pos + 1;
-        }
+        RunCursor cur{0, 0};
+        auto sel = [&](uint32_t s) { return sel4(s, x, y, z, d); };
+        run_steps(sp, cur, sp.settle, sel, [&](float r) { logistic_step<MODE>(r, v); }, [] {});
         v_settled = v;
-#pragma unroll 1
-        for (uint32_t n = 0; n < sp.accum; n++) {
-            acc.step(sel4(sp.sym[pos], x, y, z, d), v);
-            pos = (pos + 1 == sp.len) ? 0 : pos + 1;
-            if ((n & 7) == 7) acc.renorm();
-        }
+        run_steps(sp, cur, sp.accum, sel, [&](float r) { acc.step(r, v); }, [&] { acc.renorm(); });
     }
 
     float l = acc.finish(sp, x, y, z, d, v);
@@ -363,19 +391,10 @@ __device__ __forceinline__ void exponent_fast2(const SeqPlan &sp, float xa, floa
             if ((n & 7) == 7) acc.renorm();
         }
     } else {
-        uint32_t pos = 0;
-#pragma unroll 1
-        for (uint32_t n = 0; n < sp.settle; n++) {
-            settle_step(rpair(sp.sym[pos]));
-            pos = (pos + 1 == sp.len) ? 0 : pos + 1;
-        }
+        RunCursor cur{0, 0};
+        run_steps(sp, cur, sp.settle, rpair, settle_step, [] {});
         unpack2(w, vsa, vsb);
-#pragma unroll 1
-        for (uint32_t n = 0; n < sp.accum; n++) {
-            acc.step(rpair(sp.sym[pos]), w, two, one);
-            pos = (pos + 1 == sp.len) ? 0 : pos + 1;
-            if ((n & 7) == 7) acc.renorm();
-        }
+        run_steps(sp, cur, sp.accum, rpair, [&](f32x2 r) { acc.step(r, w, two, one); }, [&] { acc.renorm(); });
     }
     acc.renorm();
     float pa, pb, wa, wb;

@@ -5,12 +5,11 @@
 
 #include "kernels.cuh"
 
-// Sequence periods with a register-table instantiation.  A period p runs on the
-// smallest listed multiple of p (the host replicates the sequence); anything else
-// uses the generic per-step-select loop (0).
+// Sequence periods with a register-table instantiation: every period up to 32 symbols.
+// Longer periods use the run-length loop (0).
 #define LYAP_PERIODS(X) \
     X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) \
-    X(18) X(20) X(21) X(22) X(24) X(26) X(27) X(28) X(30) X(32)
+    X(17) X(18) X(19) X(20) X(21) X(22) X(23) X(24) X(25) X(26) X(27) X(28) X(29) X(30) X(31) X(32)
 
 namespace lyap {
 

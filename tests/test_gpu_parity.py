@@ -140,10 +140,11 @@ def test_generic_sequence_loop_equals_unrolled_periods(scene, mode):
 
 
 def test_long_sequence_against_oracle(oracle, scene):
-    """Sequences that take the generic loop (40 symbols, period 17, 44 symbols)."""
+    """Sequences longer than 32 symbols take the run-length loop (40, 39 and 44 symbols; the last
+    one starts with a run of one)."""
     prm = clone(scene[0])
     prm.d = 3.2
-    for s in ("A9B9C9D9", "A8B7", "ABBBBBBBBBBBBBBBBBBBBBBBBBBBBBBBBBBBBBBBBBBB"):
+    for s in ("A9B9C9D9", "A9A8B9B9", "ABBBBBBBBBBBBBBBBBBBBBBBBBBBBBBBBBBBBBBBBBBB", "ABCDABCDABCDABCDABCDABCDABCDABCDABCDA"):
         seq = lp.scene_convert_sequence(s)
         assert api.plan_period(seq, prm.settle, prm.accum) == 0
         want = oracle.bake(prm, seq, 12, 10, 6)
