@@ -154,6 +154,8 @@ int lyap_peer_close(void *dptr);
 int lyap_render_host(lyap_rgba *h_rgba, lyap_point *h_points /* may be NULL */, const lyap_cam *cam,
                      const lyap_params *prm, const int32_t *seq, const lyap_light *h_lights, uint32_t num_lights,
                      uint32_t width, uint32_t height, int mode, int device, unsigned long long *evals_out);
+/* Frees the device buffers and stream the host-buffer calls keep between calls. */
+void lyap_host_workspace_release(void);
 int lyap_bake_host(void *h_exps, int dtype, const lyap_params *prm, const int32_t *seq,
                    uint32_t nx, uint32_t ny, uint32_t nz, uint32_t z0, uint32_t z1, int mode, int device);
 

@@ -69,6 +69,7 @@ def lib():
     L.lyap_write_raw.argtypes = [C.c_char_p, vp, u64]
     L.lyap_format_filename.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_ulong, u32, u32, C.c_char_p, vp, vp]
     L.lyap_probe_peaks.argtypes = [vp, vp, vp, vp]
+    L.lyap_host_workspace_release.restype = None
     L.lyap_peer_alloc.argtypes = [C.POINTER(vp), u64]
     L.lyap_peer_free.argtypes = [vp]
     L.lyap_peer_export.argtypes = [vp, vp]

@@ -7,6 +7,8 @@
 // apart from a once-per-device scratch block of work-queue counters.
 #include <cuda_runtime.h>
 
+#include <time.h>
+
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -342,45 +344,98 @@ int lyap_exponent_points(float *d_out, const float *d_xyz, uint64_t n, const lya
 }
 
 // --------------------------------------------------------------- host-buffer path
+// Per-device workspace of the host-buffer calls: device buffers and a stream that live across
+// calls (cudaMalloc/cudaFree of ~80 MB per frame and their implicit synchronisations cost more
+// than the copies).  One call at a time per device; lyap_host_workspace_release() frees it.
+namespace {
+struct HostWorkspace {
+    std::mutex mu;
+    cudaStream_t stream = nullptr;
+    void *buf[4] = {nullptr, nullptr, nullptr, nullptr};   // rgba, points, lights, evals
+    size_t cap[4] = {0, 0, 0, 0};
+};
+HostWorkspace g_ws[64];
+
+cudaError_t ws_reserve(HostWorkspace &w, int slot, size_t bytes)
+{
+    if (w.cap[slot] >= bytes) return cudaSuccess;
+    if (w.buf[slot]) cudaFree(w.buf[slot]);
+    w.buf[slot] = nullptr;
+    w.cap[slot] = 0;
+    const cudaError_t e = cudaMalloc(&w.buf[slot], bytes);
+    if (e == cudaSuccess) w.cap[slot] = bytes;
+    return e;
+}
+
+double now_ms()
+{
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+} // namespace
+
+void lyap_host_workspace_release(void)
+{
+    for (int d = 0; d < 64; ++d) {
+        HostWorkspace &w = g_ws[d];
+        std::lock_guard<std::mutex> lock(w.mu);
+        bool any = w.stream != nullptr;
+        for (int k = 0; k < 4; ++k) any = any || w.buf[k];
+        if (!any) continue;
+        cudaSetDevice(d);
+        for (int k = 0; k < 4; ++k) {
+            if (w.buf[k]) cudaFree(w.buf[k]);
+            w.buf[k] = nullptr;
+            w.cap[k] = 0;
+        }
+        if (w.stream) cudaStreamDestroy(w.stream);
+        w.stream = nullptr;
+    }
+}
+
 int lyap_render_host(lyap_rgba *h_rgba, lyap_point *h_points, const lyap_cam *cam, const lyap_params *prm,
                      const int32_t *seq, const lyap_light *h_lights, uint32_t num_lights,
                      uint32_t width, uint32_t height, int mode, int device, unsigned long long *evals_out)
 {
-    if (!h_rgba || !cam || !prm || (num_lights && !h_lights)) return LYAP_ERR_BAD_ARGUMENT;
+    if (!h_rgba || !cam || !prm || (num_lights && !h_lights) || device < 0 || device >= 64) return LYAP_ERR_BAD_ARGUMENT;
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return (int)e;
+    const bool trace = getenv("LYAP_TRACE") != nullptr;   // stage timings on stderr (adds synchronisations)
     const size_t n = (size_t)width * height;
-    lyap_rgba *d_rgba = nullptr;
-    lyap_point *d_points = nullptr;
-    lyap_light *d_lights = nullptr;
-    unsigned long long *d_evals = nullptr;
+    HostWorkspace &w = g_ws[device];
+    std::lock_guard<std::mutex> lock(w.mu);
     int rc = LYAP_OK;
-    cudaStream_t s = nullptr;
+    double t0 = now_ms(), t1 = t0, t2 = t0, t3 = t0;
     do {
-        if ((e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)) != cudaSuccess) break;
-        if ((e = cudaMalloc(&d_rgba, n * sizeof(lyap_rgba))) != cudaSuccess) break;
-        if ((e = cudaMalloc(&d_points, n * sizeof(lyap_point))) != cudaSuccess) break;
-        if ((e = cudaMalloc(&d_lights, sizeof(lyap_light) * LYAP_MAX_LIGHTS)) != cudaSuccess) break;
-        if ((e = cudaMalloc(&d_evals, sizeof(unsigned long long))) != cudaSuccess) break;
+        if (!w.stream && (e = cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking)) != cudaSuccess) break;
+        if ((e = ws_reserve(w, 0, n * sizeof(lyap_rgba))) != cudaSuccess) break;
+        if ((e = ws_reserve(w, 1, n * sizeof(lyap_point))) != cudaSuccess) break;
+        if ((e = ws_reserve(w, 2, sizeof(lyap_light) * LYAP_MAX_LIGHTS)) != cudaSuccess) break;
+        if ((e = ws_reserve(w, 3, sizeof(unsigned long long))) != cudaSuccess) break;
+        cudaStream_t s = w.stream;
+        lyap_rgba *d_rgba = (lyap_rgba *)w.buf[0];
+        lyap_point *d_points = (lyap_point *)w.buf[1];
+        lyap_light *d_lights = (lyap_light *)w.buf[2];
+        unsigned long long *d_evals = (unsigned long long *)w.buf[3];
         // the reference never clears its point buffer; zero gives miss pixels a defined colour
         if ((e = cudaMemsetAsync(d_points, 0, n * sizeof(lyap_point), s)) != cudaSuccess) break;
         if ((e = cudaMemsetAsync(d_rgba, 0, n * sizeof(lyap_rgba), s)) != cudaSuccess) break;
         if ((e = cudaMemsetAsync(d_evals, 0, sizeof(unsigned long long), s)) != cudaSuccess) break;
         if (num_lights && (e = cudaMemcpyAsync(d_lights, h_lights, sizeof(lyap_light) * num_lights, cudaMemcpyHostToDevice, s)) != cudaSuccess) break;
+        if (trace) { cudaStreamSynchronize(s); t1 = now_ms(); }
         rc = lyap_render(d_rgba, d_points, cam, prm, seq, d_lights, num_lights, width, height, mode, d_evals, s);
         if (rc != LYAP_OK) break;
+        if (trace) { cudaStreamSynchronize(s); t2 = now_ms(); }
         if ((e = cudaMemcpyAsync(h_rgba, d_rgba, n * sizeof(lyap_rgba), cudaMemcpyDeviceToHost, s)) != cudaSuccess) break;
         if (h_points && (e = cudaMemcpyAsync(h_points, d_points, n * sizeof(lyap_point), cudaMemcpyDeviceToHost, s)) != cudaSuccess) break;
         unsigned long long ev = 0;
         if ((e = cudaMemcpyAsync(&ev, d_evals, sizeof ev, cudaMemcpyDeviceToHost, s)) != cudaSuccess) break;
         if ((e = cudaStreamSynchronize(s)) != cudaSuccess) break;
         if (evals_out) *evals_out = ev;
+        t3 = now_ms();
     } while (0);
-    cudaFree(d_rgba);
-    cudaFree(d_points);
-    cudaFree(d_lights);
-    cudaFree(d_evals);
-    if (s) cudaStreamDestroy(s);
+    if (trace) fprintf(stderr, "[lyap trace] render_host %ux%u: setup+H2D %.3f ms, kernel %.3f ms, D2H %.3f ms\n", width, height, t1 - t0, t2 - t1, t3 - t2);
     if (rc != LYAP_OK) return rc;
     return (int)e;
 }

@@ -12,7 +12,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 echo "== ncu full render exact"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:render_kernel -s 1 -c 1 -f -o gpurun_out/prof_render_exact python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_render_exact.log 2>&1
 echo "== ncu full render fast"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:render_kernel -s 1 -c 1 -f -o gpurun_out/prof_render_fast python bench.py --mode fast --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_render_fast.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:render_fast2_kernel -s 1 -c 1 -f -o gpurun_out/prof_render_fast python bench.py --mode fast --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_render_fast.log 2>&1
 echo "== ncu full bake fast"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:bake_kernel -s 1 -c 1 -f -o gpurun_out/prof_bake_fast python bench.py --workload bake512 --mode fast --steps 1 --warmup 1 > gpurun_out/ncu_bake_fast.log 2>&1
 ls -la gpurun_out
