@@ -312,7 +312,7 @@ def main():
                "h2d_bytes_per_step": int(224 * n_lights + 224 + 56 + seq.nbytes),
                "d2h_bytes_per_step": int(wl["w"] * wl["h"] * 4 + 8),
                "ms_per_step": dt / args.steps * 1e3, "frames_per_s": args.steps * world / dt,
-               "api": "lyap_render_host (C ABI, host buffers; alloc + H2D + kernel + D2H + sync per call)"}
+               "api": "lyap_render_host (C ABI, host buffers: H2D of lights + kernel + D2H of the frame + sync per call)"}
 
     if peer is not None:
         peer.close()
