@@ -129,12 +129,21 @@ struct Accum<kExact> {
 template <>
 struct Accum<kHost> {
     float l;
-    __device__ __forceinline__ void init() { l = 0.0f; }
+    bool odd;       // a rare logf input (0, subnormal, inf, nan) was seen: redo the sample carefully
+    bool careful;
+    LogfCtx ctx;
+    __device__ __forceinline__ void init() { l = 0.0f; odd = false; careful = false; ctx.init(); }
     __device__ __forceinline__ void step(float r, float &v)
     {
         logistic_step<kHost>(r, v);
-        float d = __fmaf_rn(-(r + r), v, r);
-        l = __fadd_rn(l, glibc_logf(fabsf(d)));
+        const float d = __fmaf_rn(-(r + r), v, r);
+        l = __fadd_rn(l, glibc_logf_speculative(d, ctx, odd));
+    }
+    __device__ __forceinline__ void step_careful(float r, float &v)
+    {
+        logistic_step<kHost>(r, v);
+        const float d = __fmaf_rn(-(r + r), v, r);
+        l = __fadd_rn(l, glibc_logf_careful(fabsf(d), ctx));
     }
     __device__ __forceinline__ void renorm() {}
     __device__ __forceinline__ float finish(const SeqPlan &sp, float, float, float, float, float)
@@ -252,6 +261,19 @@ __device__ __forceinline__ float exponent(const SeqPlan &sp, float x, float y, f
     }
 
     float l = acc.finish(sp, x, y, z, d, v);
+    if constexpr (MODE == kHost) {
+        // a zero / subnormal / non-finite derivative went through the speculative logf somewhere:
+        // redo this sample with the exact special-case handling (rare; generic loop, small code)
+        if (acc.odd) {
+            float vv = 0.5f;
+            RunCursor cur{0, 0};
+            auto sel = [&](uint32_t s) { return sel4(s, x, y, z, d); };
+            run_steps(sp, cur, sp.settle, sel, [&](float r) { logistic_step<kHost>(r, vv); }, [] {});
+            acc.l = 0.0f;
+            run_steps(sp, cur, sp.accum, sel, [&](float r) { acc.step_careful(r, vv); }, [] {});
+            l = acc.finish(sp, x, y, z, d, vv);
+        }
+    }
     // reference kernel.cu:138: an orbit sitting on v == 0.5 after settling skips the
     // accumulation and reports l = 0 / accum
     if (v_settled == 0.5f) {

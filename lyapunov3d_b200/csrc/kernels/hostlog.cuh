@@ -37,8 +37,8 @@ static __device__ const double kLogfTab[32] = {
     0x1.b2036576afce6p-1, 0x1.526e57720db08p-3,  0x1.9c2d163a1aa2dp-1, 0x1.bc2860d224770p-3,
     0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2,  0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2};
 
-// Per-block copy of the table: the index differs per lane, which shared memory
-// serves at full rate and the constant cache would serialise.
+// Per-block copy of the table: the index differs per lane, which shared memory serves at
+// full rate and the constant cache would serialise.
 static __shared__ double2 s_logf_tab[16];
 
 __device__ __forceinline__ void hostlog_init()
@@ -47,34 +47,86 @@ __device__ __forceinline__ void hostlog_init()
     __syncthreads();
 }
 
-// x must be >= +0 or NaN (callers pass |d|).
-__device__ __forceinline__ float glibc_logf(float x)
-{
-    uint32_t ix = __float_as_uint(x);
-    if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {
-        // zero, subnormal, inf or nan
-        if (ix * 2 == 0) return __int_as_float(0xff800000);          // log(0) = -inf
-        if (ix == 0x7f800000u) return x;                              // log(inf) = inf
-        if ((ix & 0x80000000u) || ix * 2 >= 0xff000000u) return __int_as_float(0x7fc00000);
-        ix = __float_as_uint(__fmul_rn(x, 8388608.0f));               // subnormal: scale by 2^23 (exact)
-        ix -= 23u << 23;
+// Polynomial, ln2 and the int->double magic as GLOBAL data: the values are loaded once per
+// sample and then live in registers.  (As literals the compiler re-materialises every 64-bit
+// constant with two uniform moves per use; as __constant__ it re-loads them per use.)
+static __device__ const double kLogfPoly[5] = {-0x1.00ea348b88334p-2, 0x1.5575b0be00b6ap-2, -0x1.ffffef20a4123p-2,
+                                               0x1.62e42fefa39efp-1, 4503601774854144.0 /* 2^52 + 2^31 */};
+
+struct LogfCtx {
+    double a0, a1, a2, ln2, magic;
+    uint32_t tab;   // shared-window address of s_logf_tab
+    __device__ __forceinline__ void init()
+    {
+        const volatile double *p = kLogfPoly;
+        a0 = p[0]; a1 = p[1]; a2 = p[2]; ln2 = p[3]; magic = p[4];
+        unsigned long long a;
+        asm volatile("cvta.to.shared.u64 %0, %1;" : "=l"(a) : "l"(s_logf_tab));
+        tab = (uint32_t)a;
     }
+};
+
+// Rare inputs: zero, subnormal, inf, nan, negative.  bit 32 of the result set: the low word is
+// the final answer; clear: the low word is the normalised bit pattern to continue with.
+static __device__ __noinline__ unsigned long long glibc_logf_special(uint32_t ix)
+{
+    const unsigned long long fin = 1ull << 32;
+    if (ix * 2 == 0) return fin | 0xff800000u;                                   // log(0) = -inf
+    if (ix == 0x7f800000u) return fin | ix;                                       // log(inf) = inf
+    if ((ix & 0x80000000u) || ix * 2 >= 0xff000000u) return fin | 0x7fc00000u;    // negative or nan
+    return __float_as_uint(__fmul_rn(__uint_as_float(ix), 8388608.0f)) - (23u << 23);   // subnormal * 2^23 (exact)
+}
+
+// The main path for a normal positive x given as its bit pattern.
+__device__ __forceinline__ float glibc_logf_bits(uint32_t ix, const LogfCtx &c)
+{
     const uint32_t tmp = ix - 0x3f330000u;
-    const int i = (tmp >> 19) & 15;
+    const uint32_t i16 = (tmp >> 15) & 0xf0u;          // table index * 16 bytes
     const int k = (int)tmp >> 23;
     const uint32_t iz = ix - (tmp & 0xff800000u);
-    const double2 t = s_logf_tab[i];
+    double invc, logc;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(invc), "=d"(logc) : "r"(c.tab + i16));
     // z = (double)asfloat(iz): iz is a normal float in [0.699, 1.399)
     const double z = __hiloint2double((int)((iz >> 3) + 0x38000000u), (int)(iz << 29));
     // (double)k without I2F: 2^52 + 2^31 + k is exact in the low word
-    const double kd = __hiloint2double(0x43300000, (int)((uint32_t)k ^ 0x80000000u)) - 4503601774854144.0;
-    const double r = __fma_rn(z, t.x, -1.0);
-    const double y0 = __fma_rn(kd, 0x1.62e42fefa39efp-1, t.y);
+    const double kd = __dsub_rn(__hiloint2double(0x43300000, (int)((uint32_t)k ^ 0x80000000u)), c.magic);
+    const double r = __fma_rn(z, invc, -1.0);
+    const double y0 = __fma_rn(kd, c.ln2, logc);
     const double r2 = __dmul_rn(r, r);
-    double y = __fma_rn(0x1.5575b0be00b6ap-2, r, -0x1.ffffef20a4123p-2);
-    y = __fma_rn(-0x1.00ea348b88334p-2, r2, y);
+    double y = __fma_rn(c.a1, r, c.a2);
+    y = __fma_rn(c.a0, r2, y);
     y = __fma_rn(y, r2, __dadd_rn(y0, r));
     return __double2float_rn(y);
+}
+
+// |x| with full glibc semantics (any input).
+__device__ __forceinline__ float glibc_logf_careful(float x, const LogfCtx &c)
+{
+    uint32_t ix = __float_as_uint(x);
+    if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {
+        const unsigned long long s = glibc_logf_special(ix);
+        if (s >> 32) return __uint_as_float((uint32_t)s);
+        ix = (uint32_t)s;
+    }
+    return glibc_logf_bits(ix, c);
+}
+
+// Speculative form for the hot loop: evaluates the main path on |x| whatever it is and records
+// in `odd` whether x was one of the rare inputs (0, subnormal, inf, nan); the caller redoes the
+// whole sample with glibc_logf_careful when the flag comes back set.
+__device__ __forceinline__ float glibc_logf_speculative(float x, const LogfCtx &c, bool &odd)
+{
+    const uint32_t ix = __float_as_uint(x) & 0x7fffffffu;
+    odd = odd || (ix - 0x00800000u >= 0x7f800000u - 0x00800000u);
+    return glibc_logf_bits(ix, c);
+}
+
+// Single-lane variant for divergent callers (shading).
+__device__ __forceinline__ float glibc_logf_lane(float x)
+{
+    LogfCtx c;
+    c.init();
+    return glibc_logf_careful(x, c);
 }
 
 } // namespace lyap

@@ -108,7 +108,7 @@ __device__ __forceinline__ float shade_log<ArithDev>(float x) { return ArithDev:
 template <>
 __device__ __forceinline__ float shade_log<ArithHost>(float x)
 {
-    return x < 0.0f ? quiet_nan() : glibc_logf(x);
+    return x < 0.0f ? quiet_nan() : glibc_logf_lane(x);
 }
 
 // kernel.cu:25-106 followed by Color::to_rgba (color.hpp:169-175)
