@@ -153,7 +153,8 @@ def run_reference(args, wl, rank):
     port.set_threads(ncpu)       # torchrun exports OMP_NUM_THREADS=1
     checker.set_threads(ncpu)
     scene = scene_for(wl, lp)
-    rows = sample_rows(wl["h"], args.cpu_rows)
+    # bounded sample: ~0.6 s per row on 16 cores; keep the whole K-step run near two minutes
+    rows = sample_rows(wl["h"], min(args.cpu_rows, max(2, 160 // max(args.steps, 1))))
     for _ in range(min(args.warmup, 1)):
         cpu_sample(checker, port, wl, scene, rows[:1], known_calls=1)
     iters, secs, calls = 0, 0.0, None
