@@ -218,7 +218,14 @@ int lyap_render_tiles(lyap_rgba *d_rgba, lyap_point *d_points, const lyap_cam *c
                          [&] { return render_blocks_per_sm_host(P); });
     if (per_sm <= 0) return (int)cudaErrorLaunchOutOfResources;
     long want_warps = g_render_warps_per_sm.load();
-    if (want_warps <= 0) want_warps = kDefaultRenderWarpsPerSM;
+    if (want_warps <= 0) {
+        // Each lane works through its rays one after the other and a ray cannot be split, so a
+        // launch ends with lanes idling while the longest rays finish.  With few rays per lane
+        // (small frames, or 1/8 of a frame per GPU) fewer persistent warps waste less in that tail
+        // than they lose in latency hiding (measured on 1/8 and 1/4 of a 1080p frame: -6 %/-10 %).
+        const unsigned long long per_sm = a.n_items / (unsigned long long)sc->sm_count;
+        want_warps = per_sm >= 6000 ? kDefaultRenderWarpsPerSM : (per_sm >= 2500 && mode != LYAP_MODE_FAST ? 12 : 8);
+    }
     int want_blocks = (int)((want_warps * 32 + kRenderThreads - 1) / kRenderThreads);
     if (want_blocks < per_sm) per_sm = want_blocks;
     unsigned long long grid = (unsigned long long)sc->sm_count * per_sm;
