@@ -60,6 +60,8 @@ int lyap_set_option(const char *key, long value);
 /* Which unrolled-period instantiation a sequence runs on: its period's smallest
  * compiled multiple, 0 for the generic loop, -1 for an invalid sequence. */
 int lyap_plan_period(const int32_t *seq, uint32_t settle, uint32_t accum);
+/* Test hook: dumps the iteration schedule built for a sequence (see csrc/abi.cu). */
+int lyap_plan_describe(const int32_t *seq, uint32_t settle, uint32_t accum, uint32_t *header, uint8_t *sym, uint8_t *rot, uint8_t *runs);
 
 /* ----------------------------------------------------------------------------
  * Host scene helpers -- same meaning as the reference functions they replace.

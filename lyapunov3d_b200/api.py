@@ -40,6 +40,7 @@ def lib():
     L.lyap_error_string.argtypes = [i32]
     L.lyap_set_option.argtypes = [C.c_char_p, C.c_long]
     L.lyap_plan_period.argtypes = [vp, u32, u32]
+    L.lyap_plan_describe.argtypes = [vp, u32, u32, vp, vp, vp, vp]
     L.lyap_params_init.argtypes = [vp, vp, vp, vp, C.c_char_p, C.c_size_t, vp, vp]
     L.lyap_params_init.restype = None
     L.lyap_scene_convert_sequence.restype = C.c_size_t
@@ -139,6 +140,19 @@ def campath_frame(f, n_frames, cam):
 def plan_period(seq, settle, accum):
     seq = np.ascontiguousarray(seq, np.int32)
     return lib().lyap_plan_period(seq.ctypes.data, settle, accum)
+
+
+def plan_describe(seq, settle, accum):
+    """The iteration schedule (SeqPlan) the library builds for a sequence; for tests."""
+    seq = np.ascontiguousarray(seq, np.int32)
+    hdr = np.zeros(11, np.uint32)
+    sym, rot, runs = np.zeros(1024, np.uint8), np.zeros(32, np.uint8), np.zeros(2048, np.uint8)
+    _check(lib().lyap_plan_describe(seq.ctypes.data, settle, accum, hdr.ctypes.data, sym.ctypes.data, rot.ctypes.data,
+                                    runs.ctypes.data), "lyap_plan_describe")
+    P, ln, sh, sp_, ap, at = (int(v) for v in hdr[:6])
+    return {"P": P, "len": ln, "settle_head": sh, "settle_periods": sp_, "accum_periods": ap, "accum_tail": at,
+            "cnt": [int(v) for v in hdr[6:10]], "sym": sym[:ln].tolist(), "rot": rot[:min(ln, 32)].tolist(),
+            "runs": runs[:2 * int(hdr[10])].reshape(-1, 2).tolist()}
 
 
 def tile_count(width, height, tile, rank, world):

@@ -167,6 +167,23 @@ int lyap_plan_period(const int32_t *seq, uint32_t settle, uint32_t accum)
     return build_plan(sp, seq, settle, accum);
 }
 
+/* Test hook: the iteration schedule a sequence is turned into.  header[0..10] = period
+ * instantiation, len, settle_head, settle_periods, accum_periods, accum_tail, cnt[0..3], n_runs;
+ * sym/rot/runs receive the arrays (sym: len bytes, rot: min(len,32), runs: 2*n_runs). */
+int lyap_plan_describe(const int32_t *seq, uint32_t settle, uint32_t accum, uint32_t *header, uint8_t *sym, uint8_t *rot, uint8_t *runs)
+{
+    SeqPlan sp;
+    const int P = build_plan(sp, seq, settle, accum);
+    if (P < 0) return LYAP_ERR_BAD_SEQUENCE;
+    const uint32_t h[11] = {(uint32_t)P, sp.len, sp.settle_head, sp.settle_periods, sp.accum_periods, sp.accum_tail,
+                            sp.cnt[0], sp.cnt[1], sp.cnt[2], sp.cnt[3], sp.n_runs};
+    memcpy(header, h, sizeof h);
+    memcpy(sym, sp.sym, sp.len);
+    memcpy(rot, sp.rot, sp.len < (uint32_t)kMaxPeriodRegs ? sp.len : (uint32_t)kMaxPeriodRegs);
+    memcpy(runs, sp.runs, 2 * sp.n_runs);
+    return LYAP_OK;
+}
+
 uint64_t lyap_tile_count(uint32_t width, uint32_t height, uint32_t tile, uint32_t rank, uint32_t world)
 {
     if (!tile || !world || rank >= world) return 0;

@@ -471,3 +471,28 @@ def test_headless_apps(tmp_path, scene):
     from PIL import Image
     png = [f for f in files if f.endswith(".png")][0]
     assert np.array_equal(np.asarray(Image.open(tmp_path / png).convert("RGB")), rgba.cpu().numpy()[..., :3])
+
+
+def test_every_period_instantiation_and_odd_iteration_counts(oracle, scene):
+    """All 32 unrolled-period kernels plus the run-length loop, with settle/accum counts that are
+    not multiples of the period (rotation, partial head and tail periods), a D symbol and d != default."""
+    rng = np.random.default_rng(5)
+    prm = clone(scene[0])
+    for period in list(range(1, 33)) + [33, 47]:
+        while True:
+            body = rng.integers(0, 4, period)
+            if period == 1 or not any(period % p == 0 and (body == np.tile(body[:p], period // p)).all() for p in range(1, period)):
+                break
+        seq = np.array(list(body) + [-1], np.int32)
+        prm.settle = int(rng.integers(0, 3 * period + 2))
+        prm.accum = int(rng.integers(1, 5 * period + 40))
+        prm.d = float(np.float32(rng.uniform(2.5, 3.9)))
+        assert api.plan_period(seq, prm.settle, prm.accum) == (period if period <= 32 else 0)
+        want = oracle.bake(prm, seq, 8, 4, 4)
+        got = lp.bake(prm, seq, 8, 4, 4, mode="host").cpu().numpy()
+        assert same_floats(got, want), (period, prm.settle, prm.accum)
+        for mode in ("exact", "fast"):
+            got = lp.bake(prm, seq, 8, 4, 4, mode=mode).cpu().numpy()
+            # short accumulations divide the summation noise by a small count: scale the tolerance
+            tol = max(BAKE_TOL, 2e-4 * 1008 / prm.accum)
+            assert close_nan(got, want, tol), (mode, period, prm.settle, prm.accum, float(np.nanmax(np.abs(got - want))))
