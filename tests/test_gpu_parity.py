@@ -496,3 +496,28 @@ def test_every_period_instantiation_and_odd_iteration_counts(oracle, scene):
             # short accumulations divide the summation noise by a small count: scale the tolerance
             tol = max(BAKE_TOL, 2e-4 * 1008 / prm.accum)
             assert close_nan(got, want, tol), (mode, period, prm.settle, prm.accum, float(np.nanmax(np.abs(got - want))))
+
+
+def test_python_cli_single_gpu(tmp_path, scene):
+    """lyapunov3d_b200.cli (the multi-GPU front end) on one GPU: same bytes as the API."""
+    import os
+    import subprocess
+    import sys
+    prm, cam, lights, n, seq = scene
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=root)
+    r = subprocess.run([sys.executable, "-m", "lyapunov3d_b200.cli", "frame", "--width", "64", "--height", "40", "--mode", "exact",
+                        "--points", "--out", str(tmp_path)], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    c = clone(cam)
+    lp.scene_cam_recalculate(c, 64, 40, 1)
+    rgba, pts, _ = lp.render(c, prm, seq, lights, n, 64, 40, mode="exact")
+    from PIL import Image
+    png = [f for f in os.listdir(tmp_path) if f.endswith(".png")][0]
+    raw = [f for f in os.listdir(tmp_path) if f.startswith("Points_")][0]
+    assert np.array_equal(np.asarray(Image.open(tmp_path / png).convert("RGB")), rgba.cpu().numpy()[..., :3])
+    assert open(tmp_path / raw, "rb").read() == pts.cpu().numpy().tobytes()
+    r = subprocess.run([sys.executable, "-m", "lyapunov3d_b200.cli", "bake", "--n", "16", "--mode", "fast", "--out", str(tmp_path / "v.raw")],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert same_floats(np.fromfile(tmp_path / "v.raw", np.float32).reshape(16, 16, 16), lp.bake(prm, seq, 16, mode="fast").cpu().numpy())
