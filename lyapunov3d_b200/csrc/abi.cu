@@ -240,8 +240,8 @@ int lyap_render_tiles(lyap_rgba *d_rgba, lyap_point *d_points, const lyap_cam *c
         // launch ends with lanes idling while the longest rays finish.  With few rays per lane
         // (small frames, or 1/8 of a frame per GPU) fewer persistent warps waste less in that tail
         // than they lose in latency hiding (measured on 1/8 and 1/4 of a 1080p frame: -6 %/-10 %).
-        const unsigned long long per_sm = a.n_items / (unsigned long long)sc->sm_count;
-        want_warps = per_sm >= 6000 ? kDefaultRenderWarpsPerSM : (per_sm >= 2500 && mode != LYAP_MODE_FAST ? 12 : 8);
+        const unsigned long long items_per_sm = a.n_items / (unsigned long long)sc->sm_count;
+        want_warps = items_per_sm >= 6000 ? kDefaultRenderWarpsPerSM : (items_per_sm >= 2500 && mode != LYAP_MODE_FAST ? 12 : 8);
     }
     int want_blocks = (int)((want_warps * 32 + kRenderThreads - 1) / kRenderThreads);
     if (want_blocks < per_sm) per_sm = want_blocks;
