@@ -27,6 +27,7 @@ namespace {
 std::atomic<long> g_force_generic{0};
 std::atomic<long> g_render_warps_per_sm{0};   // 0 = default
 std::atomic<long> g_bake_blocks_per_sm{0};    // 0 = occupancy maximum
+std::atomic<long> g_fast_redo{1};             // debug knob: 0 disables the safe re-evaluation in fast mode
 std::atomic<long> g_nvcc_normal_quirk{0};     // test knob: emulate the reference CUDA build's aliased normals
 
 constexpr int kDefaultRenderWarpsPerSM = 16;
@@ -70,6 +71,7 @@ int build_plan(SeqPlan &sp, const int32_t *seq, uint32_t settle, uint32_t accum)
     memset(&sp, 0, sizeof sp);
     sp.len = L;
     sp.fold_bias = (uint32_t)(127 + Accum<kFast>::kBias) << 23;
+    sp.redo = (uint32_t)g_fast_redo.load();
     sp.settle = settle;
     sp.accum = accum;
     for (uint32_t i = 0; i < L; ++i) sp.sym[i] = (uint8_t)seq[i % per];
@@ -156,6 +158,7 @@ int lyap_set_option(const char *key, long value)
     else if (!strcmp(key, "render_warps_per_sm")) g_render_warps_per_sm = value;
     else if (!strcmp(key, "bake_blocks_per_sm")) g_bake_blocks_per_sm = value;
     else if (!strcmp(key, "emulate_ref_nvcc_normals")) g_nvcc_normal_quirk = value;
+    else if (!strcmp(key, "fast_redo")) g_fast_redo = value;
     else return LYAP_ERR_BAD_ARGUMENT;
     return LYAP_OK;
 }

@@ -45,6 +45,7 @@ struct SeqPlan {
     uint32_t cnt[4];          // how often each symbol occurs among the accum steps
     uint32_t fold_bias;       // float bits of 2^kBias; a run-time value so that each fold's
                               // (bits & mantissa) | bias stays ONE three-input LOP3
+    uint32_t redo;            // fast mode: re-evaluate samples whose fold saw a zero exponent field (default 1)
     uint32_t n_runs;          // run-length form of the period (generic path): number of (symbol, length) pairs
     uint8_t rot[kMaxPeriodRegs];  // sym rotated left by settle_head: the order both period loops see
     uint8_t sym[kMaxSeq];         // the period as written (register-table path)
@@ -155,11 +156,18 @@ struct Accum<kHost> {
 template <>
 struct Accum<kFast> {
     // prod is kept in [2^kBias, 2^(kBias+1)) after each fold.  |1-2v| is 0 or at
-    // least 2^-24 for any float v in [0,1], and never above 1, so ten steps can
-    // take prod no lower than 2^(kBias-240) > 2^-126: no underflow is possible and
-    // a zero exponent field can only mean a true zero derivative.
+    // least 2^-24 for any float v in [0,1], and never above 1, so TEN steps can
+    // take prod no lower than 2^(kBias-240) > 2^-126: folding every <= 10 steps
+    // (kSafeFold; the run-length loop folds every <= 8) cannot underflow, and a zero
+    // exponent field then can only mean a true zero derivative.
+    // The unrolled-period loops fold every kFoldEvery = 20 steps instead, which halves
+    // the integer work: that is safe unless |1-2v| averages below 2^-12 over twenty
+    // consecutive steps (orbits within ~1e-4 of the superstable point for the whole
+    // block).  Such a sample -- like a true zero -- shows up as emin == 0 and is simply
+    // evaluated again by the guaranteed-safe loop (fast_redo below).
     static constexpr int kBias = 120;
-    static constexpr int kFoldEvery = 10;
+    static constexpr int kSafeFold = 10;
+    static constexpr int kFoldEvery = 20;
     float prod;
     int esum, emin;
     __device__ __forceinline__ void init()
@@ -200,6 +208,9 @@ struct Accum<kFast> {
 };
 
 // -------------------------------------------------------------------- driver
+// Out-of-line, rarely taken: the guaranteed-safe evaluation of one sample (defined below).
+static __device__ __noinline__ float fast_redo(const SeqPlan &sp, float x, float y, float z, float d);
+
 template <int P>
 struct PeriodUnroll {
     static constexpr int U = (P >= 11) ? 1 : (20 / (P > 0 ? P : 1));  // periods per loop body
@@ -261,6 +272,9 @@ __device__ __forceinline__ float exponent(const SeqPlan &sp, float x, float y, f
     }
 
     float l = acc.finish(sp, x, y, z, d, v);
+    if constexpr (MODE == kFast && P > 0) {
+        if (acc.emin == 0 && sp.redo) return fast_redo(sp, x, y, z, d);   // zero or underflow: ask the safe loop
+    }
     if constexpr (MODE == kHost) {
         // a zero / subnormal / non-finite derivative went through the speculative logf somewhere:
         // redo this sample with the exact special-case handling (rare; generic loop, small code)
@@ -281,6 +295,11 @@ __device__ __forceinline__ float exponent(const SeqPlan &sp, float x, float y, f
         else l = __fdiv_rn(0.0f, __uint2float_rn(sp.accum));
     }
     return l;
+}
+
+static __device__ __noinline__ float fast_redo(const SeqPlan &sp, float x, float y, float z, float d)
+{
+    return exponent<kFast, 0>(sp, x, y, z, d);
 }
 
 // ------------------------------------------------- two samples per lane (packed f32x2)
@@ -424,6 +443,11 @@ __device__ __forceinline__ void exponent_fast2(const SeqPlan &sp, float xa, floa
     unpack2(w, wa, wb);
     la = fast_finish(sp, acc.esum0, acc.emin0, pa, xa, ya, za, d, wa);
     lb = fast_finish(sp, acc.esum1, acc.emin1, pb, xb, yb, zb, d, wb);
+    if constexpr (P > 0) {
+        // zero derivative or (with the 20-step folds) a possible underflow: ask the safe loop
+        if (acc.emin0 == 0 && sp.redo) la = fast_redo(sp, xa, ya, za, d);
+        if (acc.emin1 == 0 && sp.redo) lb = fast_redo(sp, xb, yb, zb, d);
+    }
     const float zero = __fdiv_rn(0.0f, __uint2float_rn(sp.accum));
     if (vsa == -0.5f) la = zero;   // w == -0.5 <=> v == 0.5 after settling (kernel.cu:138)
     if (vsb == -0.5f) lb = zero;

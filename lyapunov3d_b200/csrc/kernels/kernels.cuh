@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(kRenderThreads) render_kernel(const __grid_con
     const unsigned lane = threadIdx.x & 31;
     RayState st;
     st.phase = kNeedRay;
-    st.sx = st.sy = st.sz = 2.0f;
+    st.sx = st.sy = st.sz = 3.0f;   // idle lanes evaluate a harmless dummy point (not 2.0: that orbit is superstable)
     bool drained = false;
     unsigned long long evals = 0;
 
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(kRenderThreads, 3) render_fast2_kernel(const _
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
         st[j].phase = kNeedRay;
-        st[j].sx = st[j].sy = st[j].sz = 2.0f;
+        st[j].sx = st[j].sy = st[j].sz = 3.0f;   // harmless dummy point for idle slots (2.0 would be the superstable orbit)
     }
     bool drained = false;
     unsigned long long evals = 0;
@@ -299,6 +299,10 @@ __global__ void __launch_bounds__(kRenderThreads, 3) render_fast2_kernel(const _
                     if (ev == kHit) normalize3<A>(st[j].Nx, st[j].Ny, st[j].Nz);
                     finish_pixel<A>(a, st[j], ev == kHit);
                     st[j].phase = kNeedRay;
+                    // park the slot on a harmless point: if it is never refilled it keeps being
+                    // evaluated, and a stale zero-derivative point would send the whole warp
+                    // through the safe re-evaluation on every remaining iteration
+                    st[j].sx = st[j].sy = st[j].sz = 3.0f;
                 }
             }
         }
