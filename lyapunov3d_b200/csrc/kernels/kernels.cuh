@@ -175,7 +175,7 @@ __device__ __forceinline__ void finish_pixel(const RenderArgs &a, const RayState
 }
 
 template <int MODE, int P>
-__global__ void __launch_bounds__(kRenderThreads) render_kernel(const __grid_constant__ RenderArgs a)
+__global__ void __launch_bounds__(kRenderThreads, 4) render_kernel(const __grid_constant__ RenderArgs a)
 {
     using A = typename ArithOf<MODE>::type;
     if constexpr (MODE == kHost) hostlog_init();
