@@ -521,3 +521,22 @@ def test_python_cli_single_gpu(tmp_path, scene):
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     assert same_floats(np.fromfile(tmp_path / "v.raw", np.float32).reshape(16, 16, 16), lp.bake(prm, seq, 16, mode="fast").cpu().numpy())
+
+
+def test_patched_reference_lyap_calculate_writes_identical_volume(tmp_path, scene):
+    """The reference's own lyap_calculate program with the kernel launch swapped for lyap_bake
+    (integration/lyap_calculate.patch, prebuilt as oracle/_ref/lyap_calculate_b200): its exps.raw
+    must equal the library's EXACT-mode 512^3 volume, which in turn is bit-identical to the
+    reference kernel's (profiles/r01_parity_report.json)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", "lyap_calculate_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/lyap_calculate_b200 not built")
+    r = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-1000:]
+    assert "Points size = 536870912" in r.stdout                      # the reference's own printf
+    vol = np.fromfile(tmp_path / "exps.raw", np.float32).reshape(512, 512, 512)
+    prm, _, _, _, seq = scene
+    assert same_floats(vol, lp.bake(prm, seq, 512, mode="exact").cpu().numpy())
