@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
     ap.add_argument("--workload", default="frame1080", choices=sorted(WORKLOADS))
     ap.add_argument("--mode", default="exact", choices=["exact", "fast", "host"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -174,6 +174,29 @@ def run_reference(args, wl, rank):
         "gpu_launches": 0}))
 
 
+def run_reference_cuda(args, wl, rank):
+    """Extra arm (not part of the driver contract): the UNMODIFIED reference kernel.cu, compiled with
+    the reference's nvcc flags for sm_100 (oracle/_ref/libref_cuda.so), timed on this GPU with CUDA
+    events around its own <<<(W/16,H/16),(16,16)>>> launch -- the kernel this library replaces."""
+    if rank != 0:
+        return
+    import lyapunov3d_b200 as lp
+    from oracle import Oracle, RefCuda
+    if not RefCuda.available() or "w" not in wl:
+        print(json.dumps({"impl": "reference-cuda", "unavailable": "oracle/_ref/libref_cuda.so not built or not a frame workload"}))
+        return
+    prm, cam, lights, n_lights, seq = scene_for(wl, lp)
+    rc = RefCuda()
+    _, _, ms = rc.render(cam, prm, seq, lights, n_lights, wl["w"], wl["h"], reps=max(1, min(args.steps, 3)))
+    # evaluations: counted by our exact-mode kernel, whose march is bit-identical to the reference kernel's
+    evals = int(lp.render(cam, prm, seq, lights, n_lights, wl["w"], wl["h"], mode="exact")[2].item())
+    val = evals * (prm.settle + prm.accum) / (ms * 1e-3) / 1e9
+    print(json.dumps({"impl": "reference-cuda", "metric": "lyapunov_giga_iters_per_s", "value": val, "unit": "Giter/s", "n_gpus": 1,
+                      "ms_per_step": ms, "higher_is_better": True, "dtype": "f32/f64 mixed (reference arithmetic)", "data": "synthetic",
+                      "config": {"workload": wl["what"], "kernel": "kernel_calc_render<<<(W/16,H/16),(16,16)>>>, best of %d" % max(1, min(args.steps, 3))},
+                      "frames_per_s": 1e3 / ms}))
+
+
 # --------------------------------------------------------------------------- our arm
 def main():
     args = parse()
@@ -183,6 +206,9 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, wl, rank)
+        return
+    if args.impl == "reference-cuda":
+        run_reference_cuda(args, wl, rank)
         return
 
     import torch
