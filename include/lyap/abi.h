@@ -150,8 +150,10 @@ int lyap_peer_open(const unsigned char *handle64, void **dptr);/* other ranks */
 int lyap_peer_close(void *dptr);
 
 /* ----------------------------------------------------------------------------
- * Whole-call convenience with HOST buffers (allocations, copies and the final
- * synchronise happen inside; this is the end-to-end path bench.py times).
+ * Whole-call convenience with HOST buffers: H2D of the lights, the kernel, D2H of the
+ * results and the final synchronise happen inside (this is the end-to-end path bench.py
+ * times).  Device buffers and a stream are kept per device between calls; one call at a
+ * time per device.  LYAP_TRACE=1 in the environment prints stage timings to stderr.
  * ------------------------------------------------------------------------- */
 int lyap_render_host(lyap_rgba *h_rgba, lyap_point *h_points /* may be NULL */, const lyap_cam *cam,
                      const lyap_params *prm, const int32_t *seq, const lyap_light *h_lights, uint32_t num_lights,
@@ -175,10 +177,11 @@ int lyap_format_filename(char *out, size_t cap, const char *prefix, unsigned lon
                          const char *sequence, const lyap_cam *cam, const lyap_params *prm);
 
 /* ----------------------------------------------------------------------------
- * Roofline probes: register-only FFMA and MUFU.LG2 loops.  Returns achieved
- * lane-operations per second over `iters` inner iterations on the current device.
+ * Roofline probes on the current device: register-only loops of eight independent chains
+ * per thread.  lyap_probe_peaks reports the achieved FFMA and MUFU.LG2 lane-operations per
+ * second (the denominators of bench.py's roofline); lyap_probe_ffma2 the same for packed
+ * fma.rn.f32x2 in scalar-equivalent lane-operations.  sm_clock_hz_est is informational.
  * ------------------------------------------------------------------------- */
-/* Same loop with packed fma.rn.f32x2 (FFMA2): scalar-equivalent lane-operations per second. */
 int lyap_probe_ffma2(double *packed_ffma_lane_ops_per_s);
 int lyap_probe_peaks(double *ffma_lane_ops_per_s, double *mufu_lane_ops_per_s, double *sm_clock_hz_est, int *sm_count);
 
