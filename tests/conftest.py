@@ -14,6 +14,18 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_sessionstart(session):
+    """A fresh checkout has no built artefacts (they are git-ignored): build the product library
+    (nvcc cross-compiles without a GPU) and the C oracle before collecting, if they are missing."""
+    from lyapunov3d_b200 import _build
+    if not os.path.exists(_build.LIB) and os.path.exists(_build.NVCC):
+        _build.build()
+    oracle_so = os.path.join(ROOT, "oracle", "liblyap_oracle.so")
+    if not os.path.exists(oracle_so):
+        import oracle
+        oracle.build()
+
+
 @pytest.fixture(scope="session")
 def oracle():
     """The C restatement of the reference hot path (test infrastructure)."""
