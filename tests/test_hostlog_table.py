@@ -1,0 +1,61 @@
+"""The glibc logf restatement used by LYAP_MODE_HOST (csrc/kernels/hostlog.cuh), pinned on the CPU.
+
+The 16-entry (invc, logc) table and the polynomial are parsed out of the CUDA header, the algorithm
+(glibc 2.39 sysdeps/ieee754/flt-32/e_logf.c) is restated in numpy float64, and the result is compared
+bit for bit with this machine's libm logf -- the function the reference's host build calls per step.
+(The fused and unfused double forms round to the same float except within ~1e-16 of a tie.)"""
+import ctypes
+import ctypes.util
+import os
+import re
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def parse_header():
+    text = open(os.path.join(ROOT, "lyapunov3d_b200", "csrc", "kernels", "hostlog.cuh")).read()
+    tab_src = text[text.index("kLogfTab[32]"):]
+    tab_src = tab_src[tab_src.index("{") + 1:tab_src.index("}")]
+    tab = [float.fromhex(t) for t in re.findall(r"-?0x[0-9a-fA-F.]+p[+-]?\d+", tab_src)]
+    assert len(tab) == 32
+    poly_src = text[text.index("kLogfPoly[5]"):]
+    poly_src = poly_src[poly_src.index("{") + 1:poly_src.index("}")]
+    poly = [float.fromhex(t) for t in re.findall(r"-?0x[0-9a-fA-F.]+p[+-]?\d+", poly_src)]
+    assert len(poly) == 4
+    return np.array(tab).reshape(16, 2), poly
+
+
+def logf_model(x, tab, poly):
+    a0, a1, a2, ln2 = poly
+    ix = x.view(np.uint32).astype(np.int64)
+    tmp = (ix - 0x3F330000) & 0xFFFFFFFF
+    i = (tmp >> 19) & 15
+    k = ((tmp.astype(np.uint32)).view(np.int32) >> 23).astype(np.float64)
+    iz = ((ix - (tmp & 0xFF800000)) & 0xFFFFFFFF).astype(np.uint32)
+    z = iz.view(np.float32).astype(np.float64)
+    invc, logc = tab[i, 0], tab[i, 1]
+    r = z * invc - 1.0
+    y0 = logc + k * ln2
+    r2 = r * r
+    y = a1 * r + a2
+    y = a0 * r2 + y
+    y = y * r2 + (y0 + r)
+    return y.astype(np.float32)
+
+
+def test_logf_restatement_equals_this_machines_libm():
+    tab, poly = parse_header()
+    libm = ctypes.CDLL(ctypes.util.find_library("m"))
+    libm.logf.restype = ctypes.c_float
+    libm.logf.argtypes = [ctypes.c_float]
+    rng = np.random.default_rng(11)
+    # normal positive floats, with emphasis on (0, 4]: the range of |r(1-2v)|
+    bits = np.concatenate([rng.integers(0x00800000, 0x7F800000, 60000), rng.integers(0x30000000, 0x40800000, 140000)]).astype(np.uint32)
+    x = bits.view(np.float32)
+    want = np.array([libm.logf(float(v)) for v in x], np.float32)
+    got = logf_model(x, tab, poly)
+    assert (got.view(np.uint32) == want.view(np.uint32)).all()
+    assert logf_model(np.array([1.0], np.float32), tab, poly)[0] == 0.0      # exact zero at x == 1, as glibc returns
+    assert tab[9, 0] == 1.0 and tab[9, 1] == 0.0
