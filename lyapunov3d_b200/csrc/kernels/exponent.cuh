@@ -14,8 +14,8 @@
 //           reference's fast-math build, so l is bit-identical to the reference
 //           kernel on the same GPU.  4 FP32 + 1 MUFU per step: SFU-bound.
 //   kFast   the derivative's magnitude is multiplied up instead:
-//           prod *= |1 - 2v'|, exponent folded out with integer ops every <= 10
-//           steps, one lg2 at the end; sum(log r) is added analytically from the
+//           prod *= |1 - 2v'|, exponent folded out with integer ops every <= 20
+//           steps (see Accum<kFast>), one lg2 at the end; sum(log r) is added analytically from the
 //           per-symbol counts.  4 FP32 per step, no MUFU in the loop: FP32-bound.
 //   kHost   IEEE adds of a glibc-exact logf per step (reference host build).
 //
