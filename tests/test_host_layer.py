@@ -126,3 +126,44 @@ def test_no_cpu_fallback():
         lp.render(cam, prm, lp.scene_convert_sequence(s), lights, n, 16, 16)
     with pytest.raises(lp.LyapError):
         lp.bake_host(prm, lp.scene_convert_sequence(s), 8)
+
+
+def test_scene_helpers_match_oracle_on_random_inputs(oracle):
+    """Product host layer vs the (reference-pinned) oracle on random cameras, lights and path
+    positions: byte-identical structs, including non-unit quaternions (the reference's
+    normalize() quirk) and tiny magnifications (the 1e-6 clamp)."""
+    rng = np.random.default_rng(2018)
+    _, cam, lights, _, _, _ = lp.params_init()
+    for _ in range(200):
+        a, b = clone(cam), clone(cam)
+        q = rng.normal(size=4) * rng.choice([1.0, 1.0, 1.0, 0.3, 2.5])
+        if rng.random() < 0.7:
+            q = q / np.linalg.norm(q)
+        mag = float(np.float32(rng.choice([0.45, 1.2, 1e-7, rng.uniform(0.01, 3.0)])))
+        pos = [float(np.float32(v)) for v in rng.uniform(-2, 8, 3)]
+        for c in (a, b):
+            c.Q.x, c.Q.y, c.Q.z, c.Q.w = (float(np.float32(v)) for v in q)
+            c.M = mag
+            c.C.x, c.C.y, c.C.z = pos
+        w, h, d = int(rng.integers(1, 4097)), int(rng.integers(1, 2161)), int(rng.integers(1, 4))
+        lp.scene_cam_recalculate(a, w, h, d)
+        oracle.cam_recalculate(b, w, h, d)
+        assert struct_bytes(a) == struct_bytes(b)
+    for _ in range(50):
+        la, lb = clone(lights), clone(lights)
+        for k in range(16):
+            q = rng.normal(size=4)
+            q /= np.linalg.norm(q)
+            for L in (la, lb):
+                L[k].Q.x, L[k].Q.y, L[k].Q.z, L[k].Q.w = (float(np.float32(v)) for v in q)
+                L[k].M = float(np.float32(0.1 + 0.1 * k))
+        lp.scene_lights_recalculate(la, 16)
+        oracle.lights_recalculate(lb, 16)
+        assert struct_bytes(la) == struct_bytes(lb)
+    for i in np.concatenate([rng.uniform(0, 1, 300), [0.0, 1.0, 1e-7, 1 - 1e-7, 0.5]]):
+        a, b = clone(cam), clone(cam)
+        lp.campath_orbit(float(i), a)
+        oracle.campath(float(i), b)
+        assert struct_bytes(a) == struct_bytes(b), i
+    for t in rng.uniform(0, 1, 100):
+        assert api.ease_in_out_quart(float(t)) == oracle.ease(float(t))
