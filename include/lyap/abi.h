@@ -28,12 +28,24 @@ enum lyap_mode {
      * the same GPU.  SFU-bound. */
     LYAP_MODE_EXACT = 0,
     /* Throughput mode: derivative magnitudes are multiplied, the exponent folded out
-     * with integer ops, log taken once per sample.  Same chaotic trajectory, bake
-     * within 1e-3; images differ where the reference's jitter PRNG decorrelates. */
+     * with integer ops, log taken once per sample.  Same chaotic trajectory; volumes
+     * within 1e-3 of the reference.  NOT an image-parity mode: with jitter on, frac(l)
+     * is the reference's PRNG and normals are differences at float-noise level, so FAST
+     * frames agree with the reference on only ~75 % of pixels.
+     * For frames use EXACT / HOST, or the HYBRID modes below when jitter == 0. */
     LYAP_MODE_FAST = 1,
     /* Parity mode against the reference's HOST build (and the CPU oracle): IEEE
      * arithmetic without contraction and a bit-exact glibc logf per step. */
     LYAP_MODE_HOST = 2,
+    /* EXACT's (resp. HOST's) hit points, normals, exponents and pixels at close to FAST's cost for
+     * scenes with prm->jitter == 0: the march samples -- whose exponents are then only
+     * compared with the three thresholds -- run on the fast evaluator, samples inside a guard band
+     * around a threshold are re-evaluated, and refinement + normals run on the parity evaluator.
+     * LyapPoint.P/N/l and RGBA equal the parity mode's; the cloud sums a and c are sums of the fast
+     * march exponents and agree to ~1e-6 relative.  With jitter != 0 the call IS the parity mode.
+     * lyap_bake / lyap_exponent_points / lyap_shade_points treat these as EXACT resp. HOST. */
+    LYAP_MODE_HYBRID = 3,
+    LYAP_MODE_HYBRID_HOST = 4,
 };
 
 enum lyap_dtype { LYAP_F32 = 0, LYAP_F16 = 1 };
@@ -47,6 +59,7 @@ enum lyap_error {
 };
 
 enum { LYAP_MAX_SEQUENCE = 1024 };
+enum { LYAP_MAX_TILE = 4096 };   /* largest tile edge lyap_render_tiles / lyap_scatter_tiles / lyap_tile_count accept */
 
 const char *lyap_version(void);
 const char *lyap_error_string(int code);
@@ -55,7 +68,11 @@ const char *lyap_error_string(int code);
  * "bake_blocks_per_sm" (cap; 0 = occupancy maximum), "force_generic" (1 = always use
  * the per-step-select exponent loop instead of a period instantiation),
  * "emulate_ref_nvcc_normals" (test knob: reproduce the normals the reference's CUDA
- * build produces under nvcc 12.9, where ls[] aliases lyap4d's abcd[]). */
+ * build produces under nvcc 12.9, where ls[] aliases lyap4d's abcd[]),
+ * "hybrid_guard_batch" (parked lanes per warp that trigger a parity pass; 0 = default),
+ * "hybrid_guard_percent" (test knob: guard band width in % of the derived bound).
+ * The knobs are process-global and read at launch time: set them before launching from
+ * several threads, not concurrently with launches. */
 int lyap_set_option(const char *key, long value);
 /* Which unrolled-period instantiation a sequence runs on: its period's smallest
  * compiled multiple, 0 for the generic loop, -1 for an invalid sequence. */
@@ -98,8 +115,9 @@ void lyap_campath_frame(uint32_t f, uint32_t n_frames, lyap_cam *cam);
  *           cudaSeq, cudaLights, num_lights)            (lyap_interactive.cu:711).
  *
  * d_rgba / d_points: width*height elements, row-major, index x + y*width.
- * seq: the HOST array scene_convert_sequence produced (the reference uploads it to
- *      cudaSeq; this library reads it on the host and bakes it into the launch).
+ * seq: the -1-terminated array scene_convert_sequence produced -- either the HOST array
+ *      (preferred: it is read on the host and baked into the launch) or the reference's
+ *      device copy `cudaSeq` (fetched with a small blocking copy per call).
  * d_lights: device array of num_lights lights, already recalculated.
  * Miss pixels leave d_points[ind] untouched and shade whatever it holds, exactly as
  * the reference does (kernel.cu:508-512): zero-fill it for defined output.
@@ -136,6 +154,14 @@ int lyap_bake(void *d_exps, int dtype, const lyap_params *prm, const int32_t *se
 /* Exponent at arbitrary points (xyz: n*3 floats on the device) -> d_out[n]. */
 int lyap_exponent_points(float *d_out, const float *d_xyz, uint64_t n, const lyap_params *prm,
                          const int32_t *seq, int mode, void *stream);
+
+/* Diagnostics in a mode's own arithmetic (EXACT: the reference CUDA build's approximate divide and
+ * square root, which a CPU cannot recompute; HOST: IEEE).  lyap_ray_probe runs the ray set-up of
+ * kernel.cu:160-315 for n pixels (d_pixels: n x {x, y}) and writes 12 floats per pixel:
+ * {hit, V.x, V.y, V.z, t0, t1, Fdt, Ndt, P0.x, P0.y, P0.z, Fdt*gradient}.  lyap_normalize_vectors
+ * applies Vec::normalize (vec3.hpp:141-154) in place to n xyz triples. */
+int lyap_ray_probe(float *d_out, const uint32_t *d_pixels, uint64_t n, const lyap_cam *cam, const lyap_params *prm, int mode, void *stream);
+int lyap_normalize_vectors(float *d_xyz, uint64_t n, int mode, void *stream);
 
 /* ----------------------------------------------------------------------------
  * Peer memory for one-process-per-GPU sharding: rank 0 allocates the result buffer and

@@ -27,7 +27,8 @@ NVCC_FLAGS = ARCH + ["-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-ccbin", 
                      "-I", os.path.join(ROOT, "include"), "-I", CSRC]
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
 
-CU = ["abi.cu", "kernels/misc.cu"] + [f"kernels/tu_{k}_{m}.cu" for k in ("render", "bake") for m in ("exact", "fast", "host")]
+CU = (["abi.cu", "kernels/misc.cu"] + [f"kernels/tu_{k}_{m}.cu" for k in ("render", "bake") for m in ("exact", "fast", "host")]
+      + ["kernels/tu_march_exact.cu", "kernels/tu_march_host.cu"])
 CPP = ["host/scene.cpp", "host/imageio.cpp"]
 APPS = ["lyap_render", "lyap_calculate"]
 BIN = os.path.join(PKG, "bin")

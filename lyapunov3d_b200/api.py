@@ -13,8 +13,8 @@ import numpy as np
 
 from .structs import MAX_LIGHTS, POINT_DTYPE, Cam, LightArray, Params
 
-MODE_EXACT, MODE_FAST, MODE_HOST = 0, 1, 2
-MODES = {"exact": MODE_EXACT, "fast": MODE_FAST, "host": MODE_HOST}
+MODE_EXACT, MODE_FAST, MODE_HOST, MODE_HYBRID, MODE_HYBRID_HOST = 0, 1, 2, 3, 4
+MODES = {"exact": MODE_EXACT, "fast": MODE_FAST, "host": MODE_HOST, "hybrid": MODE_HYBRID, "hybrid_host": MODE_HYBRID_HOST}
 F32, F16 = 0, 1
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liblyap_b200.so")
@@ -63,6 +63,8 @@ def lib():
     L.lyap_shade_points.argtypes = [vp, vp, vp, vp, u32, u64, i32, vp]
     L.lyap_bake.argtypes = [vp, i32, vp, vp, u32, u32, u32, u32, u32, i32, vp]
     L.lyap_exponent_points.argtypes = [vp, vp, u64, vp, vp, i32, vp]
+    L.lyap_ray_probe.argtypes = [vp, vp, u64, vp, vp, i32, vp]
+    L.lyap_normalize_vectors.argtypes = [vp, u64, i32, vp]
     L.lyap_render_host.argtypes = [vp, vp, vp, vp, vp, vp, u32, u32, u32, i32, i32, vp]
     L.lyap_bake_host.argtypes = [vp, i32, vp, vp, u32, u32, u32, u32, u32, i32, i32]
     L.lyap_write_ppm.argtypes = [C.c_char_p, vp, u32, u32]
@@ -265,6 +267,25 @@ def exponent_points(xyz, prm, seq, mode="exact"):
     out = torch.empty(xyz.shape[0], dtype=torch.float32, device=xyz.device)
     _check(lib().lyap_exponent_points(out.data_ptr(), xyz.data_ptr(), xyz.shape[0], C.byref(prm), seq.ctypes.data,
                                       _mode(mode), _stream_ptr(torch)), "lyap_exponent_points")
+    return out
+
+
+def ray_probe(pixels, cam, prm, mode="exact"):
+    """Ray set-up in the mode's own arithmetic: pixels int[n,2] (x, y) -> float32[n,12]
+    {hit, V(3), t0, t1, Fdt, Ndt, P0(3), Fdt*gradient}."""
+    torch = _torch()
+    px = torch.as_tensor(np.ascontiguousarray(pixels, np.uint32).view(np.int32)).cuda()
+    out = torch.empty((px.shape[0], 12), dtype=torch.float32, device=px.device)
+    _check(lib().lyap_ray_probe(out.data_ptr(), px.data_ptr(), px.shape[0], C.byref(cam), C.byref(prm), _mode(mode),
+                                _stream_ptr(torch)), "lyap_ray_probe")
+    return out
+
+
+def normalize_vectors(xyz, mode="exact"):
+    """Vec::normalize in the mode's arithmetic, on a float32 CUDA tensor [n,3] (returns a new tensor)."""
+    torch = _torch()
+    out = xyz.contiguous().float().clone()
+    _check(lib().lyap_normalize_vectors(out.data_ptr(), out.shape[0], _mode(mode), _stream_ptr(torch)), "lyap_normalize_vectors")
     return out
 
 

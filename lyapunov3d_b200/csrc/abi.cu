@@ -10,6 +10,7 @@
 #include <time.h>
 
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -29,6 +30,8 @@ std::atomic<long> g_render_warps_per_sm{0};   // 0 = default
 std::atomic<long> g_bake_blocks_per_sm{0};    // 0 = occupancy maximum
 std::atomic<long> g_fast_redo{1};             // debug knob: 0 disables the safe re-evaluation in fast mode
 std::atomic<long> g_nvcc_normal_quirk{0};     // test knob: emulate the reference CUDA build's aliased normals
+std::atomic<long> g_guard_batch{0};           // hybrid mode: parked lanes per warp that trigger a parity pass (0 = default)
+std::atomic<long> g_guard_scale{100};         // hybrid mode: guard band width in percent of the derived bound (test knob)
 
 constexpr int kDefaultRenderWarpsPerSM = 16;
 
@@ -98,6 +101,46 @@ int build_plan(SeqPlan &sp, const int32_t *seq, uint32_t settle, uint32_t accum)
     return P;
 }
 
+// The reference hands its kernels `cudaSeq`, a DEVICE copy of the -1-terminated array
+// (lyap_interactive.cu:98-109, lyap_calculate.cu:45-56).  The entry points take either: a host
+// (or managed) pointer is read in place; a device pointer is fetched with a small blocking
+// copy, so that a caller can swap the <<<>>> line alone and keep passing cudaSeq.
+struct SeqRef {
+    const int32_t *ptr = nullptr;
+    std::vector<int32_t> fetched;
+    cudaError_t err = cudaSuccess;
+    explicit SeqRef(const int32_t *seq)
+    {
+        ptr = seq;
+        if (!seq) return;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, seq) != cudaSuccess) { cudaGetLastError(); return; }   // plain host memory on old drivers
+        if (at.type != cudaMemoryTypeDevice) return;
+        // length unknown: fetch a chunk; if that runs off the end of the allocation, go element by element
+        const size_t chunk = 64;
+        fetched.assign(LYAP_MAX_SEQUENCE + 2, -1);
+        size_t have = 0;
+        bool single = false;
+        while (have <= LYAP_MAX_SEQUENCE) {
+            const size_t n = single ? 1 : chunk;
+            const size_t want = have + n <= fetched.size() ? n : fetched.size() - have;
+            cudaError_t e = cudaMemcpy(fetched.data() + have, seq + have, want * sizeof(int32_t), cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                if (single) { err = e; break; }
+                single = true;
+                continue;
+            }
+            bool done = false;
+            for (size_t i = have; i < have + want; ++i) if (fetched[i] == -1) { done = true; break; }
+            have += want;
+            if (done) break;
+        }
+        fetched.back() = -1;
+        ptr = fetched.data();
+    }
+};
+
 // ------------------------------------------------------------ per-device scratch
 struct DeviceScratch {
     int sm_count = 0;
@@ -120,6 +163,15 @@ cudaError_t scratch_for_current_device(DeviceScratch **out)
         if ((e = cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) { delete s; return e; }
         if ((e = cudaMalloc(&s->counters, sizeof(unsigned long long) * kCounterRing)) != cudaSuccess) { delete s; return e; }
         if ((e = cudaMemset(s->counters, 0, sizeof(unsigned long long) * kCounterRing)) != cudaSuccess) { delete s; return e; }
+        // hybrid mode takes its per-launch work list from the stream-ordered allocator: keep freed
+        // blocks in the pool instead of returning them to the driver at every synchronisation
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        } else {
+            cudaGetLastError();
+        }
         g_scratch[dev] = s;
     }
     *out = g_scratch[dev];
@@ -132,7 +184,23 @@ auto by_mode(int mode, F1 exact, F2 fast, F3 host) -> decltype(exact())
     return mode == LYAP_MODE_FAST ? fast() : (mode == LYAP_MODE_HOST ? host() : exact());
 }
 
-bool valid_mode(int mode) { return mode == LYAP_MODE_EXACT || mode == LYAP_MODE_FAST || mode == LYAP_MODE_HOST; }
+bool valid_mode(int mode) { return mode >= LYAP_MODE_EXACT && mode <= LYAP_MODE_HYBRID_HOST; }
+bool hybrid_mode(int mode) { return mode == LYAP_MODE_HYBRID || mode == LYAP_MODE_HYBRID_HOST; }
+// The evaluator whose results a mode reproduces (what bake / points / shade run for the hybrids).
+int parity_mode(int mode) { return mode == LYAP_MODE_HYBRID ? LYAP_MODE_EXACT : (mode == LYAP_MODE_HYBRID_HOST ? LYAP_MODE_HOST : mode); }
+
+// Half-width of the hybrid mode's guard band around a threshold `thr`.  The parity evaluators sum
+// `accum` float logarithms; each add rounds at half an ulp of the running sum, whose magnitude stays
+// below M = 2*|thr|*accum for a final exponent near thr, so the parity exponent lies within
+// ulp(M)/2 of the exact sum (the fast evaluator's own error is three orders smaller).  Twice that:
+float guard_half_width(float thr, uint32_t accum)
+{
+    double M = 2.0 * (fabs((double)thr) + 1e-3) * (double)(accum ? accum : 1);
+    if (M < 1.0) M = 1.0;
+    int e = 0;
+    frexp(M, &e);                 // M = f * 2^e, f in [0.5, 1): ulp_float(M) = 2^(e - 24)
+    return (float)ldexp(1.0, e - 24);
+}
 
 } // namespace
 
@@ -159,6 +227,8 @@ int lyap_set_option(const char *key, long value)
     else if (!strcmp(key, "bake_blocks_per_sm")) g_bake_blocks_per_sm = value;
     else if (!strcmp(key, "emulate_ref_nvcc_normals")) g_nvcc_normal_quirk = value;
     else if (!strcmp(key, "fast_redo")) g_fast_redo = value;
+    else if (!strcmp(key, "hybrid_guard_batch")) g_guard_batch = value;
+    else if (!strcmp(key, "hybrid_guard_percent")) g_guard_scale = value;
     else return LYAP_ERR_BAD_ARGUMENT;
     return LYAP_OK;
 }
@@ -189,7 +259,7 @@ int lyap_plan_describe(const int32_t *seq, uint32_t settle, uint32_t accum, uint
 
 uint64_t lyap_tile_count(uint32_t width, uint32_t height, uint32_t tile, uint32_t rank, uint32_t world)
 {
-    if (!tile || !world || rank >= world) return 0;
+    if (!tile || tile > LYAP_MAX_TILE || !world || rank >= world) return 0;
     const uint64_t tiles = (uint64_t)((width + tile - 1) / tile) * ((height + tile - 1) / tile);
     const uint64_t mine = tiles / world + (rank < tiles % world ? 1 : 0);
     return mine * tile * tile;
@@ -200,12 +270,14 @@ int lyap_render_tiles(lyap_rgba *d_rgba, lyap_point *d_points, const lyap_cam *c
                       uint32_t width, uint32_t height, uint32_t tile, uint32_t rank, uint32_t world,
                       int compact, int mode, unsigned long long *d_evals, void *stream)
 {
-    if (!d_rgba || !d_points || !cam || !prm || !valid_mode(mode) || !width || !height || !tile || !world || rank >= world)
+    if (!d_rgba || !d_points || !cam || !prm || !valid_mode(mode) || !width || !height || !tile || tile > LYAP_MAX_TILE || !world || rank >= world)
         return LYAP_ERR_BAD_ARGUMENT;
     if (num_lights > LYAP_MAX_LIGHTS || (num_lights && !d_lights)) return LYAP_ERR_BAD_ARGUMENT;
     if ((uint64_t)width * height > 0xffffffffull) return LYAP_ERR_BAD_ARGUMENT;
     RenderArgs a;
-    const int P = build_plan(a.plan, seq, prm->settle, prm->accum);
+    const SeqRef sq(seq);
+    if (sq.err != cudaSuccess) return (int)sq.err;
+    const int P = build_plan(a.plan, sq.ptr, prm->settle, prm->accum);
     if (P < 0) return LYAP_ERR_BAD_SEQUENCE;
     DeviceScratch *sc = nullptr;
     cudaError_t e = scratch_for_current_device(&sc);
@@ -233,6 +305,52 @@ int lyap_render_tiles(lyap_rgba *d_rgba, lyap_point *d_points, const lyap_cam *c
     cudaStream_t s = (cudaStream_t)stream;
     a.queue = sc->counters + (sc->next.fetch_add(1) % kCounterRing);
     if ((e = cudaMemsetAsync(a.queue, 0, sizeof(unsigned long long), s)) != cudaSuccess) return (int)e;
+    a.worklist = nullptr;
+    a.work_count = nullptr;
+
+    // Hybrid modes: with jitter the march exponents feed the jitter PRNG (kernel.cu:334-347) and
+    // every sample must be the parity evaluator's, so the call is the parity mode itself.
+    if (hybrid_mode(mode) && prm->jitter == 0.0f) {
+        if (a.n_items > 0xffffffffull) return LYAP_ERR_BAD_ARGUMENT;
+        const bool host = mode == LYAP_MODE_HYBRID_HOST;
+        const double scale = (double)g_guard_scale.load() / 100.0;
+        a.guard[0] = (float)(scale * guard_half_width(prm->opaqueThreshold, prm->accum));
+        a.guard[1] = (float)(scale * guard_half_width(prm->chaosThreshold, prm->accum));
+        a.guard[2] = (float)(scale * guard_half_width(prm->nearThreshold, prm->accum));
+        const long gb = g_guard_batch.load();
+        a.guard_batch = gb > 0 ? (uint32_t)(gb > 32 ? 32 : gb) : (host ? 8u : 4u);
+        // [count, padded to 16 bytes][work list]: stream-ordered, lives until the second launch is done
+        unsigned char *mem = nullptr;
+        if ((e = cudaMallocAsync(&mem, 16 + a.n_items * sizeof(uint32_t), s)) != cudaSuccess) return (int)e;
+        do {
+            if ((e = cudaMemsetAsync(mem, 0, 16, s)) != cudaSuccess) break;
+            a.work_count = reinterpret_cast<unsigned long long *>(mem);
+            a.worklist = reinterpret_cast<uint32_t *>(mem + 16);
+            int per_sm = host ? march_blocks_per_sm_host(P) : march_blocks_per_sm_exact(P);
+            if (per_sm <= 0) { e = cudaErrorLaunchOutOfResources; break; }
+            long want_warps = g_render_warps_per_sm.load();
+            if (want_warps > 0 && (want_warps * 32 + kRenderThreads - 1) / kRenderThreads < per_sm)
+                per_sm = (int)((want_warps * 32 + kRenderThreads - 1) / kRenderThreads);
+            unsigned long long grid = (unsigned long long)sc->sm_count * per_sm;
+            const unsigned long long max_useful = (a.n_items + 2 * kRenderThreads - 1) / (2 * kRenderThreads);
+            if (grid > max_useful) grid = max_useful;
+            e = host ? launch_march_host(P, a, (unsigned)grid, s) : launch_march_exact(P, a, (unsigned)grid, s);
+            if (e != cudaSuccess) break;
+            // second launch: refinement + normals + shading of the listed rays on the parity evaluator
+            RenderArgs b = a;
+            b.queue = sc->counters + (sc->next.fetch_add(1) % kCounterRing);
+            if ((e = cudaMemsetAsync(b.queue, 0, sizeof(unsigned long long), s)) != cudaSuccess) break;
+            per_sm = host ? render_blocks_per_sm_host(P) : render_blocks_per_sm_exact(P);
+            if (per_sm <= 0) { e = cudaErrorLaunchOutOfResources; break; }
+            grid = (unsigned long long)sc->sm_count * per_sm;
+            const unsigned long long max2 = (a.n_items + kRenderThreads - 1) / kRenderThreads;
+            if (grid > max2) grid = max2;
+            e = host ? launch_render_host(P, b, (unsigned)grid, s) : launch_render_exact(P, b, (unsigned)grid, s);
+        } while (0);
+        const cudaError_t ef = cudaFreeAsync(mem, s);
+        return (int)(e != cudaSuccess ? e : ef);
+    }
+    mode = parity_mode(mode);
 
     int per_sm = by_mode(mode, [&] { return render_blocks_per_sm_exact(P); }, [&] { return render_blocks_per_sm_fast(P); },
                          [&] { return render_blocks_per_sm_host(P); });
@@ -268,7 +386,7 @@ int lyap_render(lyap_rgba *d_rgba, lyap_point *d_points, const lyap_cam *cam, co
 int lyap_scatter_tiles(void *d_image, const void *d_compact, uint32_t elem_size, uint32_t width, uint32_t height,
                        uint32_t tile, uint32_t rank, uint32_t world, void *stream)
 {
-    if (!d_image || !d_compact || !elem_size || !tile || !world || rank >= world) return LYAP_ERR_BAD_ARGUMENT;
+    if (!d_image || !d_compact || !elem_size || !tile || tile > LYAP_MAX_TILE || !world || rank >= world) return LYAP_ERR_BAD_ARGUMENT;
     ScatterArgs a;
     a.image = (uint8_t *)d_image;
     a.compact = (const uint8_t *)d_compact;
@@ -291,6 +409,7 @@ int lyap_shade_points(lyap_rgba *d_rgba, const lyap_point *d_points, const lyap_
 {
     if (!d_rgba || !d_points || !cam || !valid_mode(mode) || num_lights > LYAP_MAX_LIGHTS) return LYAP_ERR_BAD_ARGUMENT;
     if (!count) return LYAP_OK;
+    mode = parity_mode(mode);
     ShadeArgs a;
     a.cam = *cam;
     a.rgba = d_rgba;
@@ -307,8 +426,11 @@ int lyap_bake(void *d_exps, int dtype, const lyap_params *prm, const int32_t *se
 {
     if (!d_exps || !prm || !valid_mode(mode) || !nx || !ny || !nz || z1 > nz || z0 > z1) return LYAP_ERR_BAD_ARGUMENT;
     if (dtype != LYAP_F32 && dtype != LYAP_F16) return LYAP_ERR_BAD_ARGUMENT;
+    mode = parity_mode(mode);
     BakeArgs a;
-    const int P = build_plan(a.plan, seq, prm->settle, prm->accum);
+    const SeqRef sq(seq);
+    if (sq.err != cudaSuccess) return (int)sq.err;
+    const int P = build_plan(a.plan, sq.ptr, prm->settle, prm->accum);
     if (P < 0) return LYAP_ERR_BAD_SEQUENCE;
     if (z0 == z1) return LYAP_OK;
     DeviceScratch *sc = nullptr;
@@ -351,8 +473,11 @@ int lyap_exponent_points(float *d_out, const float *d_xyz, uint64_t n, const lya
                          const int32_t *seq, int mode, void *stream)
 {
     if (!d_out || !d_xyz || !prm || !valid_mode(mode)) return LYAP_ERR_BAD_ARGUMENT;
+    mode = parity_mode(mode);
     PointsArgs a;
-    const int P = build_plan(a.plan, seq, prm->settle, prm->accum);
+    const SeqRef sq(seq);
+    if (sq.err != cudaSuccess) return (int)sq.err;
+    const int P = build_plan(a.plan, sq.ptr, prm->settle, prm->accum);
     if (P < 0) return LYAP_ERR_BAD_SEQUENCE;
     if (!n) return LYAP_OK;
     DeviceScratch *sc = nullptr;
@@ -368,6 +493,20 @@ int lyap_exponent_points(float *d_out, const float *d_xyz, uint64_t n, const lya
     e = by_mode(mode, [&] { return launch_points_exact(P, a, (unsigned)grid, s); }, [&] { return launch_points_fast(P, a, (unsigned)grid, s); },
                 [&] { return launch_points_host(P, a, (unsigned)grid, s); });
     return (int)e;
+}
+
+int lyap_ray_probe(float *d_out, const uint32_t *d_pixels, uint64_t n, const lyap_cam *cam, const lyap_params *prm, int mode, void *stream)
+{
+    if (!d_out || !d_pixels || !cam || !prm || !valid_mode(mode)) return LYAP_ERR_BAD_ARGUMENT;
+    if (!n) return LYAP_OK;
+    return (int)launch_ray_probe(parity_mode(mode) == LYAP_MODE_HOST ? kHost : kExact, d_out, d_pixels, n, *cam, *prm, (cudaStream_t)stream);
+}
+
+int lyap_normalize_vectors(float *d_xyz, uint64_t n, int mode, void *stream)
+{
+    if (!d_xyz || !valid_mode(mode)) return LYAP_ERR_BAD_ARGUMENT;
+    if (!n) return LYAP_OK;
+    return (int)launch_normalize(parity_mode(mode) == LYAP_MODE_HOST ? kHost : kExact, d_xyz, n, (cudaStream_t)stream);
 }
 
 // --------------------------------------------------------------- host-buffer path
@@ -425,7 +564,10 @@ int lyap_render_host(lyap_rgba *h_rgba, lyap_point *h_points, const lyap_cam *ca
                      const int32_t *seq, const lyap_light *h_lights, uint32_t num_lights,
                      uint32_t width, uint32_t height, int mode, int device, unsigned long long *evals_out)
 {
-    if (!h_rgba || !cam || !prm || (num_lights && !h_lights) || device < 0 || device >= 64) return LYAP_ERR_BAD_ARGUMENT;
+    if (!h_rgba || !cam || !prm || !seq || (num_lights && !h_lights) || device < 0 || device >= 64) return LYAP_ERR_BAD_ARGUMENT;
+    // reject before anything is reserved or copied: the light buffer below holds LYAP_MAX_LIGHTS entries
+    if (num_lights > LYAP_MAX_LIGHTS || !valid_mode(mode) || !width || !height || (uint64_t)width * height > 0xffffffffull)
+        return LYAP_ERR_BAD_ARGUMENT;
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return (int)e;
     const bool trace = getenv("LYAP_TRACE") != nullptr;   // stage timings on stderr (adds synchronisations)
@@ -470,7 +612,8 @@ int lyap_render_host(lyap_rgba *h_rgba, lyap_point *h_points, const lyap_cam *ca
 int lyap_bake_host(void *h_exps, int dtype, const lyap_params *prm, const int32_t *seq,
                    uint32_t nx, uint32_t ny, uint32_t nz, uint32_t z0, uint32_t z1, int mode, int device)
 {
-    if (!h_exps || !prm || z1 > nz || z0 > z1) return LYAP_ERR_BAD_ARGUMENT;
+    if (!h_exps || !prm || !seq || !nx || !ny || !nz || z1 > nz || z0 > z1 || device < 0 || device >= 64) return LYAP_ERR_BAD_ARGUMENT;
+    if (!valid_mode(mode) || (dtype != LYAP_F32 && dtype != LYAP_F16)) return LYAP_ERR_BAD_ARGUMENT;
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return (int)e;
     const size_t esz = dtype == LYAP_F16 ? 2 : 4;

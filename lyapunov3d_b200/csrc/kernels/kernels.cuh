@@ -86,10 +86,13 @@ __global__ void __launch_bounds__(256) bake_kernel(const __grid_constant__ BakeA
                               voxel_coord<MODE>((uint32_t)y1, a.ny), voxel_coord<MODE>(a.z0 + (uint32_t)q1, a.nz), a.d, l0, l1);
             if (live) {
                 const uint64_t o0 = base + i0;
-                if (!a.f16 && i1 != i0 && (o0 & 1) == 0) {
-                    reinterpret_cast<float2 *>(a.out)[o0 >> 1] = make_float2(l0, l1);
-                } else if (a.f16 && i1 != i0 && (o0 & 1) == 0) {
-                    reinterpret_cast<__half2 *>(a.out)[o0 >> 1] = __floats2half2_rn(l0, l1);
+                // the pair goes out as one vector store only where its ADDRESS is vector-aligned: the
+                // caller's pointer need only be element-aligned (a view into a larger allocation)
+                const uintptr_t addr = reinterpret_cast<uintptr_t>(a.out) + o0 * (a.f16 ? 2u : 4u);
+                if (!a.f16 && i1 != i0 && (addr & 7u) == 0) {
+                    *reinterpret_cast<float2 *>(addr) = make_float2(l0, l1);
+                } else if (a.f16 && i1 != i0 && (addr & 3u) == 0) {
+                    *reinterpret_cast<__half2 *>(addr) = __floats2half2_rn(l0, l1);
                 } else {
                     store_voxel(a, o0, l0);
                     if (i1 != i0) store_voxel(a, o0 + 1, l1);
@@ -144,6 +147,13 @@ struct RenderArgs {
     unsigned long long n_items;        // work items of this rank: its tiles * tile^2
     unsigned long long *queue;         // next work item (zeroed before launch)
     unsigned long long *evals;         // optional: += exponent evaluations
+    // hybrid mode (two launches on one stream).  The march kernel parks every ray whose
+    // march ended inside the cube in the pixel's LyapPoint slot and appends its work item here; the
+    // refine kernel (render_kernel with `worklist` set) takes its rays from the list.
+    uint32_t *worklist;
+    unsigned long long *work_count;
+    float guard[3];                    // half-width of the guard band around opaque / chaos / near threshold
+    uint32_t guard_batch;              // parked lanes per warp that trigger a parity-evaluator pass
 };
 
 constexpr int kRenderThreads = 128;
@@ -187,6 +197,8 @@ __global__ void __launch_bounds__(kRenderThreads, 4) render_kernel(const __grid_
     st.sx = st.sy = st.sz = 3.0f;   // idle lanes evaluate a harmless dummy point (not 2.0: that orbit is superstable)
     bool drained = false;
     unsigned long long evals = 0;
+    // hybrid mode's second launch: the rays are the ones the march kernel listed
+    const unsigned long long n_items = a.worklist ? *a.work_count : a.n_items;
 
     for (;;) {
         // ---- refill idle lanes from the queue
@@ -200,14 +212,18 @@ __global__ void __launch_bounds__(kRenderThreads, 4) render_kernel(const __grid_
             if ((int)lane == leader) base = atomicAdd(a.queue, (unsigned long long)n_need);
             base = __shfl_sync(full, base, leader);
             if (need) {
-                const unsigned long long k = base + __popc(m & ((1u << lane) - 1u));
+                unsigned long long k = base + __popc(m & ((1u << lane) - 1u));
                 uint32_t px, py;
-                if (k < a.n_items && item_to_pixel(a, k, px, py)) {
-                    st.out = a.compact ? (uint32_t)k : px + py * a.width;
-                    if (!ray_begin<A>(st, px, py, a.cam, a.prm)) finish_pixel<A>(a, st, false);
+                if (k < n_items) {
+                    if (a.worklist) k = a.worklist[k];
+                    if (item_to_pixel(a, k, px, py)) {
+                        st.out = a.compact ? (uint32_t)k : px + py * a.width;
+                        if (a.worklist) ray_resume<A>(st, px, py, a.cam, a.prm, a.points[st.out]);
+                        else if (!ray_begin<A>(st, px, py, a.cam, a.prm)) finish_pixel<A>(a, st, false);
+                    }
                 }
             }
-            if (base + n_need >= a.n_items) drained = true;
+            if (base + n_need >= n_items) drained = true;
         }
         const bool active = st.phase != kNeedRay;
         if (__ballot_sync(full, active) == 0) break;
@@ -305,6 +321,132 @@ __global__ void __launch_bounds__(kRenderThreads, 3) render_fast2_kernel(const _
                     st[j].sx = st[j].sy = st[j].sz = 3.0f;
                 }
             }
+        }
+    }
+
+    if (a.evals) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) evals += __shfl_xor_sync(full, evals, o);
+        if (lane == 0) atomicAdd(a.evals, evals);
+    }
+}
+
+// ---------------------------------------------------------------- hybrid mode, first launch
+// with prm.jitter == 0 a march sample's exponent is only ever COMPARED with the three
+// thresholds (kernel.cu:326,370-384), so the march -- 97.7 % of all evaluations -- can run on the
+// packed fast evaluator, two rays per lane, while refinement and normals (whose exponents end up
+// in the LyapPoint record and in the pixel) stay on the parity evaluator MODE (kExact or kHost).
+// A fast exponent that lies inside a guard band around a threshold (a.guard[], sized from the
+// rounding-error bound of the reference's float summation, abi.cu) could compare differently from
+// the parity evaluator's: that slot is parked and the warp re-evaluates its parked samples with
+// exponent<MODE> once `guard_batch` lanes hold one (or nothing else is left to do).  Hit point,
+// normal, exponent and pixel are therefore those of the parity mode; only the cloud sums a and c
+// (sums of the march exponents themselves) carry the fast evaluator's last-bit differences.
+template <class A>
+__device__ __forceinline__ void finish_miss(const RenderArgs &a, uint32_t out)
+{
+    const lyap_point pt = a.points[out];   // a miss shades whatever the caller left there (kernel.cu:508-512)
+    reinterpret_cast<uint32_t *>(a.rgba)[out] = shade_pixel<A>(pt, a.cam, a.lights, a.n_lights);
+}
+
+template <int MODE, int P>
+__global__ void __launch_bounds__(kRenderThreads, 3) march_fast2_kernel(const __grid_constant__ RenderArgs a)
+{
+    using A = typename ArithOf<MODE>::type;
+    if constexpr (MODE == kHost) hostlog_init();
+    const unsigned full = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31;
+    MarchState st[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        st[j].phase = kNeedRay;
+        st[j].Px = st[j].Py = st[j].Pz = 3.0f;   // harmless dummy point for idle slots
+    }
+    bool drained = false;
+    unsigned long long evals = 0;
+
+    auto out_of = [&](uint32_t item) {
+        uint32_t px, py;
+        item_to_pixel(a, item, px, py);
+        return a.compact ? item : px + py * a.width;
+    };
+    auto retire = [&](MarchState &s) {
+        s.phase = kNeedRay;
+        s.Px = s.Py = s.Pz = 3.0f;
+    };
+    // consume one march exponent of slot s (fast one outside the guard bands, or the parity one)
+    auto consume = [&](MarchState &s, float l) {
+        const RayEvent ev = march_consume<A>(s, l, a.prm);
+        if (ev == kContinue) return;
+        const uint32_t out = out_of(s.item);
+        if (ev == kMiss) {
+            finish_miss<A>(a, out);
+        } else {
+            lyap_point rec;
+            rec.P.x = s.Px; rec.P.y = s.Py; rec.P.z = s.Pz;
+            rec.N.x = s.t; rec.N.y = s.dt; rec.N.z = 0.0f;
+            rec.a = s.a; rec.c = s.c; rec.l = s.l;
+            a.points[out] = rec;
+            a.worklist[atomicAdd(a.work_count, 1ull)] = s.item;
+        }
+        retire(s);
+    };
+    auto in_guard = [&](float l) {
+        // NaN lands here too: the parity evaluator decides
+        return !(fabsf(l - a.prm.opaqueThreshold) >= a.guard[0] && fabsf(l - a.prm.chaosThreshold) >= a.guard[1] &&
+                 fabsf(l - a.prm.nearThreshold) >= a.guard[2]);
+    };
+
+    for (;;) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            for (;;) {
+                const bool need = st[j].phase == kNeedRay;
+                const unsigned m = __ballot_sync(full, need);
+                if (m == 0 || drained) break;
+                const int leader = __ffs(m) - 1;
+                const unsigned n_need = __popc(m);
+                unsigned long long base = 0;
+                if ((int)lane == leader) base = atomicAdd(a.queue, (unsigned long long)n_need);
+                base = __shfl_sync(full, base, leader);
+                if (need) {
+                    const unsigned long long k = base + __popc(m & ((1u << lane) - 1u));
+                    uint32_t px, py;
+                    if (k < a.n_items && item_to_pixel(a, k, px, py)) {
+                        st[j].item = (uint32_t)k;
+                        if (!ray_begin<A>(st[j], px, py, a.cam, a.prm)) {
+                            finish_miss<A>(a, a.compact ? (uint32_t)k : px + py * a.width);
+                            retire(st[j]);
+                        }
+                    }
+                }
+                if (base + n_need >= a.n_items) drained = true;
+            }
+        }
+        const bool fast0 = st[0].phase == kMarchFirst || st[0].phase == kMarch;
+        const bool fast1 = st[1].phase == kMarchFirst || st[1].phase == kMarch;
+        const bool park0 = (st[0].phase & kGuardBit) != 0, park1 = (st[1].phase & kGuardBit) != 0;
+        const bool any_fast = __ballot_sync(full, fast0 || fast1) != 0;
+        const unsigned parked = __popc(__ballot_sync(full, park0 || park1));
+        if (!any_fast && parked == 0) break;
+
+        if (any_fast && parked < a.guard_batch) {
+            float l[2];
+            exponent_fast2<P>(a.plan, st[0].Px, st[0].Py, st[0].Pz, st[1].Px, st[1].Py, st[1].Pz, a.prm.d, l[0], l[1]);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                if (j == 0 ? fast0 : fast1) {
+                    ++evals;
+                    if (in_guard(l[j])) st[j].phase |= kGuardBit;
+                    else consume(st[j], l[j]);
+                }
+            }
+        } else {
+            // one parked sample per lane through the parity evaluator (slot 0 first)
+            const float x = park0 ? st[0].Px : st[1].Px, y = park0 ? st[0].Py : st[1].Py, z = park0 ? st[0].Pz : st[1].Pz;
+            const float l = exponent<MODE, P>(a.plan, x, y, z, a.prm.d);
+            if (park0) { st[0].phase &= ~kGuardBit; consume(st[0], l); }
+            else if (park1) { st[1].phase &= ~kGuardBit; consume(st[1], l); }
         }
     }
 

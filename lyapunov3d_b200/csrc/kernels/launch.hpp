@@ -24,8 +24,16 @@ LYAP_DECLARE_MODE(exact)
 LYAP_DECLARE_MODE(fast)
 LYAP_DECLARE_MODE(host)
 
+// hybrid mode's march kernel (packed fast evaluator + parity evaluator NAME for the guard bands)
+cudaError_t launch_march_exact(int P, const RenderArgs &a, unsigned grid, cudaStream_t s);
+cudaError_t launch_march_host(int P, const RenderArgs &a, unsigned grid, cudaStream_t s);
+int march_blocks_per_sm_exact(int P);
+int march_blocks_per_sm_host(int P);
+
 cudaError_t launch_shade(int mode, const ShadeArgs &a, unsigned grid, cudaStream_t s);
 cudaError_t launch_scatter(const ScatterArgs &a, unsigned grid, cudaStream_t s);
+cudaError_t launch_ray_probe(int mode, float *out, const uint32_t *pixels, uint64_t n, const lyap_cam &cam, const lyap_params &prm, cudaStream_t s);
+cudaError_t launch_normalize(int mode, float *xyz, uint64_t n, cudaStream_t s);
 cudaError_t probe_peaks(double *ffma_ops, double *mufu_ops, double *clock_hz, int *sms);
 cudaError_t probe_ffma2(double *lane_ops);
 

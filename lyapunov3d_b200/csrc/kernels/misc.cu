@@ -39,6 +39,49 @@ cudaError_t launch_scatter(const ScatterArgs &a, unsigned grid, cudaStream_t s)
     return cudaGetLastError();
 }
 
+// ---- diagnostics: the ray set-up and the normalisation in a mode's own arithmetic ----------
+// What a parity test cannot recompute on the CPU in EXACT mode (div.approx / sqrt.approx results).
+template <class A>
+__global__ void __launch_bounds__(128) ray_probe_kernel(float *out, const uint32_t *pixels, uint64_t n, const __grid_constant__ lyap_cam cam,
+                                                        const __grid_constant__ lyap_params prm)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    RayState st;
+    const bool hit = ray_begin<A>(st, pixels[2 * i], pixels[2 * i + 1], cam, prm);
+    float *o = out + 12 * i;
+    o[0] = hit ? 1.0f : 0.0f;
+    if (!hit) { for (int k = 1; k < 12; ++k) o[k] = 0.0f; return; }
+    o[1] = st.Vx; o[2] = st.Vy; o[3] = st.Vz; o[4] = st.t; o[5] = st.t1; o[6] = st.Fdt; o[7] = st.Ndt;
+    o[8] = st.Px; o[9] = st.Py; o[10] = st.Pz; o[11] = A::mul(st.Fdt, prm.gradient);
+}
+
+template <class A>
+__global__ void __launch_bounds__(128) normalize_kernel(float *xyz, uint64_t n)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+    normalize3<A>(x, y, z);
+    xyz[3 * i] = x; xyz[3 * i + 1] = y; xyz[3 * i + 2] = z;
+}
+
+cudaError_t launch_ray_probe(int mode, float *out, const uint32_t *pixels, uint64_t n, const lyap_cam &cam, const lyap_params &prm, cudaStream_t s)
+{
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    if (mode == kHost) ray_probe_kernel<ArithHost><<<grid, 128, 0, s>>>(out, pixels, n, cam, prm);
+    else ray_probe_kernel<ArithDev><<<grid, 128, 0, s>>>(out, pixels, n, cam, prm);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_normalize(int mode, float *xyz, uint64_t n, cudaStream_t s)
+{
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    if (mode == kHost) normalize_kernel<ArithHost><<<grid, 128, 0, s>>>(xyz, n);
+    else normalize_kernel<ArithDev><<<grid, 128, 0, s>>>(xyz, n);
+    return cudaGetLastError();
+}
+
 // ---- roofline probes ------------------------------------------------------------
 // Register-only loops: 8 independent chains per thread so the pipes, not latency,
 // set the pace.  The kernels also report elapsed SM cycles so the caller can turn

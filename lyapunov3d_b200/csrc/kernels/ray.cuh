@@ -46,6 +46,23 @@ struct RayState {
     float mag, lprev, Nx, Ny, Nz;
 };
 
+// The march-only part of a ray (hybrid mode's first kernel): the sample point of a march step is
+// the point on the ray itself, and nothing of the refinement or the normal is needed yet.
+struct MarchState {
+    int phase;               // kNeedRay, kMarchFirst, kMarch; bit kGuardBit: parked, wants the parity evaluator
+    uint32_t item;           // work item (-> pixel and output slot) of the ray in flight
+    float Px, Py, Pz;
+    float Vx, Vy, Vz;
+    float t, t1;
+    float dt, Fdt, Ndt;
+    float a, c, l;
+    bool near;
+};
+constexpr int kGuardBit = 0x100;
+
+__device__ __forceinline__ void set_sample(RayState &st) { st.sx = st.Px; st.sy = st.Py; st.sz = st.Pz; }
+__device__ __forceinline__ void set_sample(MarchState &) {}
+
 template <class A>
 __device__ __forceinline__ void normalize3(float &x, float &y, float &z)
 {
@@ -172,17 +189,24 @@ __device__ __forceinline__ uint32_t shade_pixel(const lyap_point &pt, const lyap
 // kernel.cu:160-318 up to (not including) the first exponent.  Returns false when
 // the ray misses the cube (the reference's `return 1`, :262-264).
 template <class A>
-__device__ __forceinline__ bool ray_begin(RayState &st, uint32_t px, uint32_t py, const lyap_cam &cam, const lyap_params &prm)
+__device__ __forceinline__ void ray_direction(float &Vx, float &Vy, float &Vz, uint32_t px, uint32_t py, const lyap_cam &cam)
 {
     const float fx = __uint2float_rn(px), fy = __uint2float_rn(py);
     // V = S0 + SDX*sx + SDY*sy  (dev: two fma per component)
-    float Vx = A::madd(cam.SDY.x, fy, A::madd(cam.SDX.x, fx, cam.S0.x));
-    float Vy = A::madd(cam.SDY.y, fy, A::madd(cam.SDX.y, fx, cam.S0.y));
-    float Vz = A::madd(cam.SDY.z, fy, A::madd(cam.SDX.z, fx, cam.S0.z));
+    Vx = A::madd(cam.SDY.x, fy, A::madd(cam.SDX.x, fx, cam.S0.x));
+    Vy = A::madd(cam.SDY.y, fy, A::madd(cam.SDX.y, fx, cam.S0.y));
+    Vz = A::madd(cam.SDY.z, fy, A::madd(cam.SDX.z, fx, cam.S0.z));
     normalize3<A>(Vx, Vy, Vz);
     Vx = A::div(Vx, cam.M);
     Vy = A::div(Vy, cam.M);
     Vz = A::div(Vz, cam.M);
+}
+
+template <class A, class S>
+__device__ __forceinline__ bool ray_begin(S &st, uint32_t px, uint32_t py, const lyap_cam &cam, const lyap_params &prm)
+{
+    float Vx, Vy, Vz;
+    ray_direction<A>(Vx, Vy, Vz, px, py, cam);
 
     const float C[3] = {cam.C.x, cam.C.y, cam.C.z};
     const float V[3] = {Vx, Vy, Vz};
@@ -244,7 +268,7 @@ __device__ __forceinline__ bool ray_begin(RayState &st, uint32_t px, uint32_t py
     st.Ndt = A::div(Fdt, prm.nearMultiplier);
     st.near = false;
 
-    st.sx = st.Px; st.sy = st.Py; st.sz = st.Pz;
+    set_sample(st);
     st.phase = kMarchFirst;
     return true;
 }
@@ -252,8 +276,8 @@ __device__ __forceinline__ bool ray_begin(RayState &st, uint32_t px, uint32_t py
 enum RayEvent { kContinue = 0, kHit = 1, kMiss = 2 };
 
 // One march step (kernel.cu:334-363).  Returns kMiss when the ray leaves the cube.
-template <class A>
-__device__ __forceinline__ RayEvent march_step(RayState &st, const lyap_params &prm)
+template <class A, class S>
+__device__ __forceinline__ RayEvent march_step(S &st, const lyap_params &prm)
 {
     float step = st.dt;
     if (prm.jitter != 0.0f) {
@@ -265,9 +289,32 @@ __device__ __forceinline__ RayEvent march_step(RayState &st, const lyap_params &
     st.Px = A::madd(st.Vx, step, st.Px);
     st.t = A::add(st.t, step);
     if (st.t > st.t1) return kMiss;
-    st.sx = st.Px; st.sy = st.Py; st.sz = st.Pz;
+    set_sample(st);
     st.phase = kMarch;
     return kContinue;
+}
+
+// :370-384 the bookkeeping every march sample gets before the loop test: cloud accumulation and
+// the near/far step switch.
+template <class A, class S>
+__device__ __forceinline__ void march_account(S &st, float l, const lyap_params &prm)
+{
+    if (l > prm.chaosThreshold) st.c = A::add(st.c, l);
+    else if (l > prm.opaqueThreshold) st.a = A::add(st.a, l);
+    if (l <= prm.nearThreshold && !st.near) { st.near = true; st.dt = st.Ndt; }
+    else if (l > prm.nearThreshold && st.near) { st.near = false; st.dt = st.Fdt; }
+}
+
+// Hybrid mode, first kernel: consume the exponent of a march sample.  kContinue: the ray moved on
+// to its next march sample; kMiss: it left the cube; kHit: the march loop ended inside the cube
+// (kernel.cu:393) -- refinement and normal are left to the second kernel.
+template <class A>
+__device__ __forceinline__ RayEvent march_consume(MarchState &st, float l, const lyap_params &prm)
+{
+    if (st.phase == kMarch) march_account<A>(st, l, prm);
+    st.l = l;
+    if (l > prm.opaqueThreshold) return march_step<A>(st, prm);
+    return st.t > st.t1 ? kMiss : kHit;
 }
 
 template <class A>
@@ -313,6 +360,24 @@ __device__ __forceinline__ RayEvent refine_begin(RayState &st, const lyap_params
     return kContinue;
 }
 
+// Hybrid mode, second kernel: pick a ray up where the march kernel left it.  The march kernel
+// parks its state in the pixel's own LyapPoint slot (P = point on the ray, N = (t, dt, -), a, c, l);
+// the direction is recomputed from the pixel (same operations, same bits).
+template <class A>
+__device__ __forceinline__ void ray_resume(RayState &st, uint32_t px, uint32_t py, const lyap_cam &cam, const lyap_params &prm,
+                                           const lyap_point &rec)
+{
+    ray_direction<A>(st.Vx, st.Vy, st.Vz, px, py, cam);
+    st.Px = rec.P.x; st.Py = rec.P.y; st.Pz = rec.P.z;
+    st.t = rec.N.x;
+    st.dt = rec.N.y;
+    st.t1 = st.t;            // t <= t1 was established before the hand-over
+    st.Fdt = st.Ndt = st.dt; // the step switch belongs to the march
+    st.near = false;
+    st.a = rec.a; st.c = rec.c; st.l = rec.l;
+    refine_begin<A>(st, prm);
+}
+
 // Consume the exponent `l` of the pending sample.  On kHit st.{P,a,c,l} hold the
 // LyapPoint fields (kernel.cu:479-483) and st.N the un-normalised central differences.
 template <class A>
@@ -320,11 +385,7 @@ __device__ __forceinline__ RayEvent ray_advance(RayState &st, float l, const lya
 {
     switch (st.phase) {
     case kMarch:
-        // :370-384 cloud accumulation and near/far step switch
-        if (l > prm.chaosThreshold) st.c = A::add(st.c, l);
-        else if (l > prm.opaqueThreshold) st.a = A::add(st.a, l);
-        if (l <= prm.nearThreshold && !st.near) { st.near = true; st.dt = st.Ndt; }
-        else if (l > prm.nearThreshold && st.near) { st.near = false; st.dt = st.Fdt; }
+        march_account<A>(st, l, prm);
         // fall through to the loop test
     case kMarchFirst:
         st.l = l;

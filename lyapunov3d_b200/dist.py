@@ -210,13 +210,20 @@ class PeerBuffer:
             self.view((self.nbytes,), "|u1").tensor().zero_()
 
     def close(self):
+        """Importers unmap first, then a barrier, then the owner frees: cudaFree of an exported
+        allocation while another process still has it open is undefined behaviour."""
         L = api.lib()
-        if self.ptr:
-            if self.world > 1:
-                torch.cuda.synchronize()
-                dist.barrier(group=self.group)
-            (L.lyap_peer_free if self.rank == 0 else L.lyap_peer_close)(self.ptr)
-            self.ptr = 0
+        if not self.ptr:
+            return
+        ptr, self.ptr = self.ptr, 0
+        if self.world > 1:
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)      # every rank's kernels have finished storing
+            rc = L.lyap_peer_close(ptr) if self.rank != 0 else 0
+            dist.barrier(group=self.group)      # every importer has closed its mapping
+            api._check(rc, "lyap_peer_close")
+        if self.rank == 0:
+            api._check(L.lyap_peer_free(ptr), "lyap_peer_free")
 
 
 def bake_sharded_peer(volume, prm, seq, nx, ny, nz, mode="fast", f16=False, group=None):

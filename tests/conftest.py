@@ -14,6 +14,30 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def _on_gpu_box():
+    """A box that is supposed to have a GPU: the NVIDIA device nodes or nvidia-smi exist."""
+    import shutil
+    return os.path.exists("/dev/nvidiactl") or os.path.exists("/dev/nvidia0") or shutil.which("nvidia-smi") is not None
+
+
+def pytest_collection_modifyitems(config, items):
+    """`gpu`-marked tests are SKIPPED where there is no CUDA device, so that a plain `pytest tests`
+    on a CPU-only box is green or genuinely red.  One test is exempt and fails loudly instead when
+    the box looks like a GPU box (device nodes present) but CUDA does not come up:
+    test_gpu_parity.py::test_cuda_extension_loaded."""
+    try:
+        import torch
+        have = torch.cuda.is_available()
+    except Exception:
+        have = False
+    if have:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device here (gpu-marked tests run on the B200 box)")
+    for item in items:
+        if "gpu" in item.keywords and not (item.name == "test_cuda_extension_loaded" and _on_gpu_box()):
+            item.add_marker(skip)
+
+
 def pytest_sessionstart(session):
     """A fresh checkout has no built artefacts (they are git-ignored): build the product library
     (nvcc cross-compiles without a GPU) and the C oracle before collecting, if they are missing."""

@@ -26,8 +26,10 @@ PIXEL_FRAC = 0.995     # >= 99.5 % of pixels
 
 
 def need_gpu():
+    """gpu-marked tests are skipped by conftest.py where there is no CUDA device; the one exempt
+    test (test_cuda_extension_loaded) fails here if a box with NVIDIA device nodes has no CUDA."""
     if not torch.cuda.is_available():
-        pytest.fail("these tests need a CUDA device (run with -m gpu on the B200 box)")
+        pytest.fail("this looks like a GPU box but CUDA is unavailable: the hot path has no CPU fallback")
 
 
 @pytest.fixture(scope="module")
@@ -299,6 +301,226 @@ def test_miss_pixels_shade_the_callers_point_buffer(golden):
     assert np.array_equal(rgba.cpu().numpy()[miss], shaded[miss])      # and shaded as they are
 
 
+# ------------------------------------------- BASELINE sizes against the reference kernel
+def test_config2_full_1080p_frame_vs_reference_cuda_kernel(refcuda, scene):
+    """BASELINE config 2 at its own size: the 1920x1080 default frame from the unmodified reference
+    kernel (3.9 s on a B200) against EXACT mode.  P/a/c/l of EVERY pixel bit-identical; with the
+    nvcc-normal emulation on, every 36-byte record and every pixel identical."""
+    prm, cam, lights, n, seq = scene
+    w, h = 1920, 1080
+    c = clone(cam)
+    lp.scene_cam_recalculate(c, w, h, 1)
+    ref_rgba, ref_pts, _ = refcuda.render(c, prm, seq, lights, n, w, h)
+    pts = points_np(lp.render(c, prm, seq, lights, n, w, h, mode="exact")[1])
+    for f in ("P", "a", "c", "l"):
+        assert same_floats(pts[f], ref_pts[f]), f
+    api.set_option("emulate_ref_nvcc_normals", 1)
+    try:
+        rgba_q, pts_q, _ = lp.render(c, prm, seq, lights, n, w, h, mode="exact")
+    finally:
+        api.set_option("emulate_ref_nvcc_normals", 0)
+    assert point_rows_equal(points_np(pts_q), ref_pts).all()
+    assert np.array_equal(rgba_q.cpu().numpy(), ref_rgba)
+
+
+def test_config4_full_512_bake_vs_reference_cuda_kernel(refcuda, scene):
+    """BASELINE config 4 at its own size: kernel_calc_volume<<<(64,64,64),(8,8,8)>>> of the
+    unmodified reference against EXACT (bit for bit) and FAST (1e-3 absolute, NaN == NaN)."""
+    prm, _, _, _, seq = scene
+    vref, _ = refcuda.bake(prm, seq, 512)
+    assert same_floats(lp.bake(prm, seq, 512, mode="exact").cpu().numpy(), vref)
+    vf = lp.bake(prm, seq, 512, mode="fast").cpu().numpy()
+    nan = np.isnan(vref)
+    assert np.array_equal(np.isnan(vf), nan)
+    assert float(np.abs(vf[~nan] - vref[~nan]).max()) <= BAKE_TOL
+
+
+def test_config3_shape_long_sequence_frame_vs_reference_cuda_kernel(refcuda, scene):
+    """BASELINE config 3's scene (A6B6C6, 72+4032) at 480x270 against the reference kernel."""
+    prm, cam, lights, n, _ = scene
+    p3 = clone(prm)
+    p3.settle, p3.accum = 72, 4032
+    s3 = lp.scene_convert_sequence("A6B6C6")
+    w, h = 480, 270
+    c = clone(cam)
+    lp.scene_cam_recalculate(c, w, h, 1)
+    ref_rgba, ref_pts, _ = refcuda.render(c, p3, s3, lights, n, w, h)
+    api.set_option("emulate_ref_nvcc_normals", 1)
+    try:
+        rgba_q, pts_q, _ = lp.render(c, p3, s3, lights, n, w, h, mode="exact")
+    finally:
+        api.set_option("emulate_ref_nvcc_normals", 0)
+    assert point_rows_equal(points_np(pts_q), ref_pts).all()
+    assert np.array_equal(rgba_q.cpu().numpy(), ref_rgba)
+
+
+@pytest.mark.parametrize("mode", ["exact", "host"])
+def test_default_normals_are_central_differences_of_the_modes_own_exponent(scene, mode):
+    """The shipping default of EXACT mode computes the INTENDED normals (kernel.cu:456-473), which the
+    reference's CUDA build under nvcc 12.9 does not, so there is no reference image
+    to hold them to.  Direct check instead, on every hit pixel: N must equal, bit for bit,
+    normalize(l(P + mag e_k) - l(P - mag e_k)) with l from lyap_exponent_points in the same mode,
+    mag = dt * gradient for the far or the near step, and normalisation in the mode's arithmetic;
+    and shading that record with lyap_shade_points must give the frame's RGBA."""
+    prm, cam, lights, n, seq = scene
+    w, h = 96, 64
+    c = clone(cam)
+    lp.scene_cam_recalculate(c, w, h, 1)
+    rgba, pts_t, _ = lp.render(c, prm, seq, lights, n, w, h, mode=mode)
+    pts = points_np(pts_t).reshape(-1)
+    ys, xs = np.divmod(np.arange(w * h), w)
+    probe = api.ray_probe(np.stack([xs, ys], 1), c, prm, mode=mode).cpu().numpy()
+    hit = (pts["P"] != 0).any(-1)
+    assert hit.sum() > 0.5 * w * h
+    P = pts["P"][hit].astype(np.float32)
+    g = np.float32(prm.gradient)
+    matched = np.zeros(int(hit.sum()), bool)
+    for dt in (probe[hit, 6], probe[hit, 7]):                      # far step, near step
+        mag = (dt.astype(np.float32) * g).astype(np.float32)        # one rounded float multiply in both builds
+        samples = np.repeat(P[:, None, :], 6, axis=1)
+        for k in range(3):
+            samples[:, 2 * k, k] = P[:, k] - mag
+            samples[:, 2 * k + 1, k] = P[:, k] + mag
+        l = lp.exponent_points(torch.from_numpy(samples.reshape(-1, 3)).cuda(), prm, seq, mode=mode).cpu().numpy().reshape(-1, 6)
+        d = (l[:, 1::2] - l[:, 0::2]).astype(np.float32)
+        N = api.normalize_vectors(torch.from_numpy(d).cuda(), mode=mode).cpu().numpy()
+        matched |= ((N.view(np.uint32) == pts["N"][hit].view(np.uint32)) | (np.isnan(N) & np.isnan(pts["N"][hit]))).all(-1)
+    assert matched.all(), float(matched.mean())
+    assert torch.equal(lp.shade_points(pts_t, c, lights, n, mode=mode), rgba)
+
+
+# ------------------------------------------------------------------- hybrid modes
+def _jitter_free_cases(golden, scene):
+    prm, cam, lights, n, seq = scene
+    cases = []
+    g_cam, g_prm, g_lights, g_n, g_seq, g_rgba, g_pts = frame_inputs(golden["frames"], "nojitter_32")
+    assert g_prm.jitter == 0.0
+    cases.append(("nojitter_32", g_cam, g_prm, g_lights, g_n, lp.scene_convert_sequence(g_seq), 32, 32))
+    p = clone(prm)
+    p.jitter = 0.0
+    c = clone(cam)
+    lp.scene_cam_recalculate(c, 256, 256, 1)
+    cases.append(("default_256_jitter0", c, p, lights, n, seq, 256, 256))
+    p3 = clone(p)
+    p3.settle, p3.accum = 72, 4032
+    c3 = clone(cam)
+    lp.scene_cam_recalculate(c3, 96, 54, 1)
+    cases.append(("long_96x54_jitter0", c3, p3, lights, n, lp.scene_convert_sequence("A6B6C6"), 96, 54))
+    p4 = clone(p)
+    p4.stepMethod, p4.nearThreshold, p4.chaosThreshold = 1, -0.7, -0.6     # near switch and alpha band in play
+    c4 = clone(cam)
+    lp.scene_cam_recalculate(c4, 80, 48, 1)
+    cases.append(("method1_thresholds_80x48", c4, p4, lights, n, seq, 80, 48))
+    return cases
+
+
+@pytest.mark.parametrize("hybrid,parity", [("hybrid", "exact"), ("hybrid_host", "host")])
+def test_hybrid_mode_reproduces_its_parity_mode(golden, scene, hybrid, parity):
+    """jitter == 0 -> march on the packed fast evaluator (guard-banded), refinement and
+    normals on the parity evaluator.  P, N, l of every record and every pixel must be bit-identical
+    to the parity mode's, the evaluation count equal, the cloud sums a/c equal to 1e-5 relative."""
+    for name, cam, prm, lights, n, seq, w, h in _jitter_free_cases(golden, scene):
+        want_rgba, want_pts, want_ev = lp.render(cam, prm, seq, lights, n, w, h, mode=parity)
+        got_rgba, got_pts, got_ev = lp.render(cam, prm, seq, lights, n, w, h, mode=hybrid)
+        a, b = points_np(got_pts), points_np(want_pts)
+        for f in ("P", "N", "l"):
+            assert same_floats(a[f], b[f]), (name, f, float(np.mean(a[f].view(np.uint32) == b[f].view(np.uint32))))
+        assert torch.equal(got_rgba, want_rgba), name
+        assert int(got_ev.item()) == int(want_ev.item()), name
+        for f in ("a", "c"):
+            assert np.allclose(a[f], b[f], rtol=1e-5, atol=1e-5, equal_nan=True), (name, f)
+
+
+def test_hybrid_host_mode_matches_reference_host_build(golden):
+    """The golden no-jitter frame of the unmodified reference (host-compiled): hybrid_host reproduces
+    hit point, normal, exponent and pixel of every pixel."""
+    cam, prm, lights, n_lights, seq_s, want_rgba, want_pts = frame_inputs(golden["frames"], "nojitter_32")
+    rgba, pts, _ = lp.render(cam, prm, lp.scene_convert_sequence(seq_s), lights, n_lights, 32, 32, mode="hybrid_host")
+    got = points_np(pts)
+    for f in ("P", "N", "l"):
+        assert same_floats(got[f], want_pts[f]), f
+    assert np.array_equal(rgba.cpu().numpy(), want_rgba)
+
+
+def test_hybrid_mode_with_jitter_is_the_parity_mode(scene):
+    prm, cam, lights, n, seq = scene
+    assert prm.jitter != 0.0
+    c = clone(cam)
+    lp.scene_cam_recalculate(c, 64, 40, 1)
+    a = lp.render(c, prm, seq, lights, n, 64, 40, mode="exact")
+    b = lp.render(c, prm, seq, lights, n, 64, 40, mode="hybrid")
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and int(a[2].item()) == int(b[2].item())
+
+
+def test_hybrid_mode_tiles_and_guard_knobs(scene):
+    """Tile sharding (in place and compact) composes to the single-launch frame; the frame does not depend
+    on how parked samples are batched; without guard bands the frame stays within the image tolerance."""
+    prm, cam, lights, n, seq = scene
+    p = clone(prm)
+    p.jitter = 0.0
+    w, h, tile, world = 100, 52, 8, 3
+    c = clone(cam)
+    lp.scene_cam_recalculate(c, w, h, 1)
+    full_rgba, full_pts, full_ev = lp.render(c, p, seq, lights, n, w, h, mode="hybrid")
+    rgba, pts = torch.zeros_like(full_rgba), torch.zeros_like(full_pts)
+    rgba2, pts2 = torch.zeros_like(full_rgba), torch.zeros_like(full_pts)
+    ev = 0
+    for r in range(world):
+        ev += int(lp.render(c, p, seq, lights, n, w, h, mode="hybrid", tile=tile, rank=r, world=world, rgba=rgba, points=pts)[2].item())
+        c_rgba, c_pts, _ = lp.render(c, p, seq, lights, n, w, h, mode="hybrid", tile=tile, rank=r, world=world, compact=True)
+        api.scatter_tiles(rgba2, c_rgba, w, h, tile, r, world)
+        api.scatter_tiles(pts2, c_pts, w, h, tile, r, world)
+    assert torch.equal(rgba, full_rgba) and torch.equal(pts, full_pts) and ev == int(full_ev.item())
+    assert torch.equal(rgba2, full_rgba) and torch.equal(pts2, full_pts)
+    for batch in (1, 32):
+        api.set_option("hybrid_guard_batch", batch)
+        try:
+            r2, p2, _ = lp.render(c, p, seq, lights, n, w, h, mode="hybrid")
+        finally:
+            api.set_option("hybrid_guard_batch", 0)
+        assert torch.equal(r2, full_rgba) and torch.equal(p2, full_pts), batch
+    api.set_option("hybrid_guard_percent", 0)
+    try:
+        r3 = lp.render(c, p, seq, lights, n, w, h, mode="hybrid")[0]
+    finally:
+        api.set_option("hybrid_guard_percent", 100)
+    assert frac_within(r3.cpu().numpy(), full_rgba.cpu().numpy(), PIXEL_TOL) >= PIXEL_FRAC
+
+
+def test_device_resident_sequence_is_accepted(scene):
+    """The reference passes cudaSeq, a DEVICE copy of the sequence (lyap_interactive.cu:711,
+    lyap_calculate.cu:72): the entry points take that pointer as well as the host array."""
+    import ctypes as C
+    prm, cam, lights, n, seq = scene
+    d_seq = torch.from_numpy(np.ascontiguousarray(seq, np.int32)).cuda()
+    want = lp.bake(prm, seq, 16, mode="exact")
+    out = torch.zeros_like(want)
+    api._check(api.lib().lyap_bake(out.data_ptr(), api.F32, C.byref(prm), d_seq.data_ptr(), 16, 16, 16, 0, 16, api.MODE_EXACT,
+                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)), "lyap_bake(device seq)")
+    assert torch.equal(out.view(torch.int32), want.view(torch.int32))
+    long_seq = lp.scene_convert_sequence("A9B9C9D9" * 6)          # 240 symbols: more than one fetch chunk
+    d_long = torch.from_numpy(np.ascontiguousarray(long_seq, np.int32)).cuda()
+    want = lp.bake(prm, long_seq, 8, mode="fast")
+    out = torch.zeros_like(want)
+    api._check(api.lib().lyap_bake(out.data_ptr(), api.F32, C.byref(prm), d_long.data_ptr(), 8, 8, 8, 0, 8, api.MODE_FAST,
+                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)), "lyap_bake(device seq, long)")
+    assert torch.equal(out.view(torch.int32), want.view(torch.int32))
+
+
+def test_bake_into_element_aligned_views(scene):
+    """FAST mode stores voxel pairs as one vector where the ADDRESS allows it: an output pointer that is
+    only element-aligned (a view at an odd offset of a larger allocation) must work and give the same bits."""
+    prm, _, _, _, seq = scene
+    for dtype, tdt in (("f32", torch.float32), ("f16", torch.float16)):
+        want = lp.bake(prm, seq, 20, 6, 4, mode="fast", dtype=dtype)
+        big = torch.zeros(20 * 6 * 4 + 3, dtype=tdt, device="cuda")
+        view = big[1:1 + 20 * 6 * 4].view(4, 6, 20)
+        assert view.data_ptr() % (2 * view.element_size()) != 0
+        lp.bake(prm, seq, 20, 6, 4, mode="fast", dtype=dtype, out=view)
+        assert torch.equal(view.view(torch.int16 if dtype == "f16" else torch.int32), want.view(torch.int16 if dtype == "f16" else torch.int32))
+        assert float(big[0]) == 0.0 and float(big[-1]) == 0.0 and float(big[-2]) == 0.0
+
+
 # ------------------------------------------------------------ partitioning / e2e
 @pytest.mark.parametrize("mode", ["exact", "host"])
 def test_tile_partition_is_bit_identical(scene, mode):
@@ -441,6 +663,16 @@ def test_render_bad_arguments(scene):
         lp.render(cam, prm, seq, lights, n, 8, 8, mode=5)
     with pytest.raises(lp.LyapError):
         lp.render(cam, prm, seq, lights, n, 8, 8, tile=8, rank=3, world=2)
+    with pytest.raises(lp.LyapError):
+        lp.render(cam, prm, seq, lights, n, 8, 8, tile=65536, rank=0, world=1)
+    assert api.tile_count(64, 64, 65536, 0, 1) == 0
+    # host-buffer calls reject bad arguments BEFORE touching their device workspace (17 lights would
+    # overrun the 16-entry light buffer)
+    for kw in (dict(n_lights=17), dict(w=0), dict(mode=9)):
+        with pytest.raises(lp.LyapError):
+            lp.render_host(cam, prm, seq, lights, kw.get("n_lights", n), kw.get("w", 8), 8, mode=kw.get("mode", "exact"))
+    with pytest.raises(lp.LyapError):
+        lp.bake_host(prm, seq, 8, device=99)
 
 
 def test_headless_apps(tmp_path, scene):
