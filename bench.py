@@ -1,28 +1,35 @@
 #!/usr/bin/env python
 """bench.py -- headline measurement of the Lyapunov hot path (contract: see the task brief).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload frame1080|frame4k|bake512] [--mode exact|fast|host]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|reference-cuda]
+                    [--workload frame1080|frame4k|bake512] [--mode exact|fast|host|hybrid|hybrid_host]
+                    [--jitter J] [--no-subrecords] [--no-cpu-baseline] [--no-reference-cuda]
 
-One "step" = one frame of BASELINE.json's configs[1] (1920x1080, default params/scene:
-sequence BCABA, 18 settle + 1008 accumulate iterations per sample) rendered by ONE GPU.
-With N GPUs every rank renders one such frame per step (whole frames dealt to ranks, as
-the reference's animation driver would; no communication inside the render) and the
-frames are gathered to rank 0 over NCCL inside the timed region: weak scaling.
+One "step" = ONE frame of BASELINE.json's configs[1] (1920x1080, default params/scene: sequence
+BCABA, 18 settle + 1008 accumulate iterations per sample).  With N GPUs the SAME frame is cut into
+8x8-pixel tiles dealt round-robin to the ranks (north_star: "load-balanced interleaved image tiles");
+every rank's kernel stores its tiles straight into rank 0's frame over NVLink (CUDA IPC peer mapping),
+so there is no gather step: STRONG scaling, value(N) / value(1) is the speed-up of one frame.  Rank 0
+checks, outside the timed region, that the assembled frame equals its own single-GPU render byte for byte.
 
-metric  = Giga-iterations/s: logistic-map steps (settle + accumulate) of all exponent
-          evaluations the frame needed, counted by the kernel, per second.
-value   = kernel path with device-resident buffers (CUDA events, max over ranks).
-e2e     = the same frame through the C-ABI host-buffer call lyap_render_host()
-          (allocation, H2D of lights, kernel, D2H of the RGBA frame into pinned memory).
-roofline= the render kernel against the measured MUFU.LG2 issue peak (exact mode is
-          SFU-bound: one lg2.approx per accumulate step) resp. the measured FFMA peak
-          (fast mode); peaks are measured live by lyap_probe_peaks().
-cpu_baseline = the CPU oracle (C restatement, OpenMP, all host threads) on a bounded
-          sample of rows of the same frame.
+metric  = Giga-iterations/s: logistic-map steps (settle + accumulate) of all exponent evaluations the
+          frame needed, counted by the kernels, per second.
+value   = kernel path with device-resident buffers (CUDA events on the launching stream, max over ranks).
+e2e     = the same frame through the public host-buffer API: N=1 the C-ABI call lyap_render_host()
+          (H2D of the lights, kernel, D2H of the frame into pinned memory, sync); N>1 the peer-sharded
+          render plus rank 0's D2H of the assembled frame.
+roofline= the dominant kernel against the measured MUFU.LG2 issue peak (exact: one lg2.approx per
+          accumulate step, SFU-bound) resp. the measured FFMA peak (fast / hybrid); peaks measured live
+          by lyap_probe_peaks().
+cpu_baseline = the CPU oracle (C restatement, OpenMP, all host threads) on a bounded sample of rows.
+reference_cuda = the UNMODIFIED reference kernel.cu (nvcc --use_fast_math, sm_100; oracle/_ref/libref_cuda.so)
+          timed on this GPU with CUDA events around its own <<<(W/16,H/16),(16,16)>>> launch (N=1 only).
+sub     = the north-star's other multi-GPU configs, measured the same way in the same run:
+          frame4k (3840x2160, A6B6C6, 72+4032, interleaved tiles) and bake512 (512^3, z-slabs written
+          straight into rank 0's volume), each with ms, Giter/s, speed-up base and the byte-equality check.
 
---impl reference times the reference's own CPU implementation (oracle/_ref/libref_host.so,
-the unmodified sources host-compiled; the C restatement if that is absent) the same way.
+--impl reference times the reference's own CPU implementation (oracle/_ref/libref_host.so, the unmodified
+sources host-compiled; the C restatement if that is absent) on sampled rows of the same frame.
 """
 import argparse
 import json
@@ -41,6 +48,7 @@ WORKLOADS = {
     "frame4k": dict(w=3840, h=2160, seq="A6B6C6", settle=72, accum=4032, what="3840x2160 frame, A6B6C6, 72+4032 iterations"),
     "bake512": dict(n=512, seq="BCABA", settle=18, accum=1008, what="512^3 voxel bake, default params"),
 }
+TILE = 8
 
 
 def parse():
@@ -50,8 +58,11 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
     ap.add_argument("--workload", default="frame1080", choices=sorted(WORKLOADS))
-    ap.add_argument("--mode", default="exact", choices=["exact", "fast", "host"])
+    ap.add_argument("--mode", default="exact", choices=["exact", "fast", "host", "hybrid", "hybrid_host"])
+    ap.add_argument("--jitter", type=float, default=None, help="override prm.jitter (hybrid modes need 0)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-cuda", action="store_true")
+    ap.add_argument("--no-subrecords", action="store_true")
     ap.add_argument("--cpu-rows", type=int, default=12, help="rows of the frame in the CPU sample")
     return ap.parse_args()
 
@@ -101,13 +112,23 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------ scene setup
-def scene_for(wl, lp):
-    prm, cam, lights, n_lights, _, _ = lp.params_init()
+def scene_for(wl, host, jitter=None):
+    """The workload's scene from a host layer with the reference's interface: `host` is the product
+    package (our arm) or the host-compiled reference itself (reference arm)."""
+    prm, cam, lights, n_lights, _, _ = host.params_init()
     prm.settle, prm.accum = wl["settle"], wl["accum"]
-    lp.scene_lights_recalculate(lights, n_lights)
-    seq = lp.scene_convert_sequence(wl["seq"])
-    if "w" in wl:
-        lp.scene_cam_recalculate(cam, wl["w"], wl["h"], 1)
+    if jitter is not None:
+        prm.jitter = jitter
+    if hasattr(host, "scene_lights_recalculate"):
+        host.scene_lights_recalculate(lights, n_lights)
+        seq = host.scene_convert_sequence(wl["seq"])
+        if "w" in wl:
+            host.scene_cam_recalculate(cam, wl["w"], wl["h"], 1)
+    else:
+        host.lights_recalculate(lights, n_lights)
+        seq = host.convert_sequence(wl["seq"])
+        if "w" in wl:
+            host.cam_recalculate(cam, wl["w"], wl["h"], 1)
     return prm, cam, lights, n_lights, seq
 
 
@@ -135,24 +156,30 @@ def cpu_sample(checker, counter, wl, scene, rows, known_calls=None):
     return calls * (prm.settle + prm.accum), dt, calls
 
 
+def host_threads():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
 # --------------------------------------------------------------------- reference arm
 def run_reference(args, wl, rank):
+    """The reference's own CPU implementation of the path, nothing of this repo's product on it: the
+    scene comes from the reference's params_init / scene_* (host-compiled), the rows from its raymarch /
+    shade; the C restatement only counts evaluations, outside the timed part."""
     if rank != 0:
         return
     if "w" not in wl:
         print(json.dumps({"impl": "reference", "unavailable": "reference arm implemented for frame workloads"}))
         return
-    import lyapunov3d_b200 as lp
     from oracle import Oracle, RefHost
     port = Oracle()
     if RefHost.available():
         checker, kind = RefHost(), "reference"
     else:
         checker, kind = port, "port"
-    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    ncpu = host_threads()
     port.set_threads(ncpu)       # torchrun exports OMP_NUM_THREADS=1
     checker.set_threads(ncpu)
-    scene = scene_for(wl, lp)
+    scene = scene_for(wl, checker, args.jitter)
     # bounded sample: ~0.6 s per row on 16 cores; keep the whole K-step run near two minutes
     rows = sample_rows(wl["h"], min(args.cpu_rows, max(2, 160 // max(args.steps, 1))))
     for _ in range(min(args.warmup, 1)):
@@ -163,41 +190,211 @@ def run_reference(args, wl, rank):
         iters += i
         secs += s
     val = iters / secs / 1e9
-    sample = f"{len(rows)} evenly spaced rows of the frame per step ({len(rows) * wl['w']} pixels)"
+    sample = (f"{len(rows)} evenly spaced rows of the frame per step ({len(rows) * wl['w']} pixels); the metric is per "
+              "iteration, so a row sample measures the same Giter/s as the whole frame would")
     print(json.dumps({
         "impl": "reference", "metric": "lyapunov_giga_iters_per_s", "value": val, "unit": "Giter/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["what"], "sample": sample},
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["what"], "sample": sample, "scene_from": "the reference's own params_init/scene_* (host-compiled)"
+                   if kind == "reference" else "the C restatement's params_init/scene_*"},
         "cpu_baseline": {"value": val, "unit": "Giter/s", "cores": port.threads(), "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "Giter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
 
+def time_reference_cuda(wl, scene, evals, reps):
+    """The unmodified reference kernel on this GPU (checker library, timed as a reported baseline)."""
+    from oracle import RefCuda
+    if not RefCuda.available() or "w" not in wl:
+        return None
+    prm, cam, lights, n_lights, seq = scene
+    _, _, ms = RefCuda().render(cam, prm, seq, lights, n_lights, wl["w"], wl["h"], reps=reps)
+    return {"ms": ms, "giter_s": evals * (prm.settle + prm.accum) / (ms * 1e-3) / 1e9, "frames_per_s": 1e3 / ms,
+            "kernel": "kernel_calc_render<<<(W/16,H/16),(16,16)>>> of the unmodified kernel.cu, nvcc --use_fast_math -arch=sm_100, "
+                      "best of %d launch(es), CUDA events" % reps}
+
+
 def run_reference_cuda(args, wl, rank):
-    """Extra arm (not part of the driver contract): the UNMODIFIED reference kernel.cu, compiled with
-    the reference's nvcc flags for sm_100 (oracle/_ref/libref_cuda.so), timed on this GPU with CUDA
-    events around its own <<<(W/16,H/16),(16,16)>>> launch -- the kernel this library replaces."""
+    """Extra arm (not part of the driver contract): the reference CUDA kernel alone."""
     if rank != 0:
         return
     import lyapunov3d_b200 as lp
-    from oracle import Oracle, RefCuda
-    if not RefCuda.available() or "w" not in wl:
-        print(json.dumps({"impl": "reference-cuda", "unavailable": "oracle/_ref/libref_cuda.so not built or not a frame workload"}))
+    scene = scene_for(wl, lp, args.jitter)
+    prm, cam, lights, n_lights, seq = scene
+    if "w" not in wl:
+        print(json.dumps({"impl": "reference-cuda", "unavailable": "not a frame workload"}))
         return
-    prm, cam, lights, n_lights, seq = scene_for(wl, lp)
-    rc = RefCuda()
-    _, _, ms = rc.render(cam, prm, seq, lights, n_lights, wl["w"], wl["h"], reps=max(1, min(args.steps, 3)))
     # evaluations: counted by our exact-mode kernel, whose march is bit-identical to the reference kernel's
     evals = int(lp.render(cam, prm, seq, lights, n_lights, wl["w"], wl["h"], mode="exact")[2].item())
-    val = evals * (prm.settle + prm.accum) / (ms * 1e-3) / 1e9
-    print(json.dumps({"impl": "reference-cuda", "metric": "lyapunov_giga_iters_per_s", "value": val, "unit": "Giter/s", "n_gpus": 1,
-                      "ms_per_step": ms, "higher_is_better": True, "dtype": "f32/f64 mixed (reference arithmetic)", "data": "synthetic",
-                      "config": {"workload": wl["what"], "kernel": "kernel_calc_render<<<(W/16,H/16),(16,16)>>>, best of %d" % max(1, min(args.steps, 3))},
-                      "frames_per_s": 1e3 / ms}))
+    rc = time_reference_cuda(wl, scene, evals, max(1, min(args.steps, 3)))
+    if rc is None:
+        print(json.dumps({"impl": "reference-cuda", "unavailable": "oracle/_ref/libref_cuda.so not built"}))
+        return
+    print(json.dumps({"impl": "reference-cuda", "metric": "lyapunov_giga_iters_per_s", "value": rc["giter_s"], "unit": "Giter/s", "n_gpus": 1,
+                      "ms_per_step": rc["ms"], "higher_is_better": True, "dtype": "f32/f64 mixed (reference arithmetic)", "data": "synthetic",
+                      "config": {"workload": wl["what"], "kernel": rc["kernel"]}, "frames_per_s": rc["frames_per_s"]}))
 
 
 # --------------------------------------------------------------------------- our arm
+class Runner:
+    """One workload on this rank's GPU: step() queues one step on the current stream and returns the
+    device counter of exponent evaluations this rank performed; check() compares the sharded result
+    on rank 0 with a single-GPU run."""
+
+    def __init__(self, wl, mode, jitter, rank, world, dev):
+        import torch
+        import lyapunov3d_b200 as lp
+        from lyapunov3d_b200 import api
+        from lyapunov3d_b200 import dist as ld
+        self.torch, self.lp, self.api, self.ld = torch, lp, api, ld
+        self.wl, self.mode, self.rank, self.world, self.dev = wl, mode, rank, world, dev
+        self.scene = scene_for(wl, lp, jitter)
+        self.prm, self.cam, self.lights, self.n_lights, self.seq = self.scene
+        self.iters_per_eval = self.prm.settle + self.prm.accum
+        self.d_lights = api.upload_lights(self.lights, dev)
+        self.frame = "w" in wl
+        self.peers = []
+        if self.frame:
+            w, h = wl["w"], wl["h"]
+            self.units = w * h
+            self.out_bytes = w * h * 40                     # 4 B RGBA + 36 B LyapPoint per pixel
+            if world == 1:
+                self.rgba = torch.zeros((h, w, 4), dtype=torch.uint8, device=dev)
+                self.pts = torch.zeros((h, w, 36), dtype=torch.uint8, device=dev)
+            else:
+                # rank 0 owns the frame; every rank's kernel stores its tiles into it over NVLink
+                self.p_rgba = ld.PeerBuffer(w * h * 4)
+                self.p_pts = ld.PeerBuffer(w * h * 36)
+                self.peers = [self.p_rgba, self.p_pts]
+        else:
+            n = wl["n"]
+            self.units = n ** 3
+            self.out_bytes = n ** 3 * 4
+            self.z0, self.z1 = ld.slab_range(n, rank, world)
+            if world == 1:
+                self.vol = torch.zeros((n, n, n), dtype=torch.float32, device=dev)
+            else:
+                self.p_vol = ld.PeerBuffer(n ** 3 * 4)     # the full volume lives on rank 0 only
+                self.peers = [self.p_vol]
+
+    def step(self):
+        torch, lp, api, ld, wl = self.torch, self.lp, self.api, self.ld, self.wl
+        import torch.distributed as dist
+        if self.frame:
+            w, h = wl["w"], wl["h"]
+            if self.world == 1:
+                self.pts.zero_()     # the frame contract: miss pixels shade a zeroed LyapPoint
+                return lp.render(self.cam, self.prm, self.seq, self.d_lights, self.n_lights, w, h, mode=self.mode,
+                                 rgba=self.rgba, points=self.pts)[2]
+            self.p_pts.zero_()       # rank 0 clears the shared point buffer ...
+            torch.cuda.current_stream().synchronize()
+            dist.barrier()           # ... before any rank's kernel may store into it
+            ev = torch.zeros(1, dtype=torch.int64, device=self.dev)
+            ld.render_frame_sharded_peer(self.p_rgba, self.p_pts, self.cam, self.prm, self.seq, self.d_lights, self.n_lights,
+                                         w, h, mode=self.mode, tile=TILE, evals=ev)   # kernel + stream sync + barrier
+            return ev
+        n = wl["n"]
+        if self.world == 1:
+            lp.bake(self.prm, self.seq, n, mode=self.mode, out=self.vol)
+        else:
+            ld.bake_sharded_peer(self.p_vol, self.prm, self.seq, n, n, n, mode=self.mode)
+        return torch.tensor([(self.z1 - self.z0) * n * n], device=self.dev)
+
+    def check(self):
+        """Rank 0: the result assembled from all ranks' shards == this GPU's own single-launch result."""
+        torch, lp, wl = self.torch, self.lp, self.wl
+        import torch.distributed as dist
+        if self.world == 1:
+            return {"checked": False, "note": "single GPU: nothing to assemble"}
+        res = None
+        if self.rank == 0:
+            if self.frame:
+                w, h = wl["w"], wl["h"]
+                one_rgba, one_pts, _ = lp.render(self.cam, self.prm, self.seq, self.d_lights, self.n_lights, w, h, mode=self.mode)
+                got_rgba = self.p_rgba.view((h, w, 4), "|u1").tensor()
+                got_pts = self.p_pts.view((h, w, 36), "|u1").tensor()
+                res = {"checked": True, "rgba_bytes_equal": bool(torch.equal(got_rgba, one_rgba)),
+                       "points_bytes_equal": bool(torch.equal(got_pts, one_pts)),
+                       "checksum_rgba": int(got_rgba.to(torch.int64).sum().item())}
+                res["equal_to_single_gpu"] = res["rgba_bytes_equal"] and res["points_bytes_equal"]
+            else:
+                n = wl["n"]
+                one = lp.bake(self.prm, self.seq, n, mode=self.mode)
+                got = self.p_vol.view((n, n, n), "<f4").tensor()
+                eq = bool(torch.equal(got.view(torch.int32), one.view(torch.int32)))
+                res = {"checked": True, "volume_bytes_equal": eq, "equal_to_single_gpu": eq}
+            torch.cuda.synchronize()
+        dist.barrier()
+        return res
+
+    def close(self):
+        for p in self.peers:
+            p.close()
+        self.peers = []
+
+
+def timed_run(run, steps, warmup, flush, sampler=None):
+    """W warm-up steps, then K timed steps bracketed by barrier + synchronize; CUDA events around the
+    whole region and around each step; max over ranks.  Returns a dict of totals."""
+    import torch
+    import torch.distributed as dist
+    world = run.world
+    for _ in range(max(warmup, 0)):
+        run.step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    k1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    t_wall = time.perf_counter()
+    e0.record()
+    ev_list = []
+    for i in range(steps):
+        flush.zero_()                 # L2 flush between timed iterations (inside the timed region)
+        k0[i].record()
+        ev_list.append(run.step())
+        k1[i].record()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall_ms = (time.perf_counter() - t_wall) * 1e3
+    clocks = sampler.stop() if sampler else None
+    ms = e0.elapsed_time(e1)
+    step_ms = sum(a.elapsed_time(b) for a, b in zip(k0, k1)) / steps
+    evals = sum(int(e.item()) for e in ev_list)
+    stats = torch.tensor([ms, float(evals), step_ms], dtype=torch.float64, device=run.dev)
+    if world > 1:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, step_ms, total_evals = float(mx[0]), float(mx[2]), float(sm[1])
+    else:
+        total_evals = float(evals)
+    total_iters = total_evals * run.iters_per_eval
+    return {"ms": ms, "ms_per_step": ms / steps, "step_ms": step_ms, "total_evals": total_evals, "total_iters": total_iters,
+            "giter_s": total_iters / (ms * 1e-3) / 1e9, "wall_ms": wall_ms, "clocks": clocks}
+
+
+def sub_record(name, mode, steps, warmup, rank, world, dev, flush):
+    """One of the north-star's other configs, measured like the headline (strong scaling)."""
+    run = Runner(WORKLOADS[name], mode, None, rank, world, dev)
+    t = timed_run(run, steps, warmup, flush)
+    chk = run.check()
+    run.close()
+    rec = {"workload": WORKLOADS[name]["what"], "mode": mode, "steps": steps, "warmup": warmup, "ms": t["ms_per_step"],
+           "giter_s": t["giter_s"], "scaling": "strong", "shard_check": chk,
+           "partition": ("%dx%d tiles round-robin over ranks" % (TILE, TILE)) if run.frame else "contiguous z-slabs"}
+    rec["frames_per_s" if run.frame else "volumes_per_s"] = 1e3 / t["ms_per_step"]
+    return rec
+
+
 def main():
     args = parse()
     wl = WORKLOADS[args.workload]
@@ -222,177 +419,159 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    scene = scene_for(wl, lp)
-    prm, cam, lights, n_lights, seq = scene
-    iters_per_eval = prm.settle + prm.accum
-    d_lights = api.upload_lights(lights, dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
-    from lyapunov3d_b200 import dist as ld
-    peer = None
-    if "w" in wl:
-        w, h = wl["w"], wl["h"]
-        rgba = torch.zeros((h, w, 4), dtype=torch.uint8, device=dev)
-        pts = torch.zeros((h, w, 36), dtype=torch.uint8, device=dev)
-        frame_bytes = w * h * 4
-        if world > 1:
-            # rank 0 owns one RGBA slot per rank; every rank's kernel stores its frame straight
-            # into its slot over NVLink (CUDA IPC peer mapping): there is no gather step
-            peer = ld.PeerBuffer(frame_bytes * world)
-
-        def step():
-            pts.zero_()     # the frame contract: miss pixels shade a zeroed LyapPoint
-            if world == 1:
-                return lp.render(cam, prm, seq, d_lights, n_lights, w, h, mode=args.mode, rgba=rgba, points=pts)[2]
-            ev = torch.zeros(1, dtype=torch.int64, device=dev)
-            api.render_into(peer.ptr + rank * frame_bytes, pts.data_ptr(), cam, prm, seq, d_lights, n_lights, w, h,
-                            mode=args.mode, evals=ev)
-            torch.cuda.current_stream().synchronize()
-            dist.barrier()          # rank 0 may consume all frames of the step from here on
-            return ev
-        launches_per_step = 1
-        units = w * h
-    else:
-        n = wl["n"]
-        z0, z1 = ld.slab_range(n, rank, world)     # z-slab sharding: strong scaling
-        if world > 1:
-            peer = ld.PeerBuffer(n ** 3 * 4)       # the full volume lives on rank 0 only
-        else:
-            vol = torch.zeros((n, n, n), dtype=torch.float32, device=dev)
-
-        def step():
-            if world == 1:
-                lp.bake(prm, seq, n, mode=args.mode, out=vol)
-            else:
-                ld.bake_sharded_peer(peer, prm, seq, n, n, n, mode=args.mode)
-            return torch.tensor([(z1 - z0) * n * n], device=dev)
-        launches_per_step = 1
-        units = n ** 3
-
-    for _ in range(max(args.warmup, 0)):
-        ev = step()
+    run = Runner(wl, args.mode, args.jitter, rank, world, dev)
+    prm, cam, lights, n_lights, seq = run.scene
+    iters_per_eval = run.iters_per_eval
+    # peaks first (also warms the clocks), then the timed region
+    for _ in range(min(args.warmup, 1)):
+        run.step()
     torch.cuda.synchronize()
     peaks = api.probe_peaks() if rank == 0 else None
-
     sampler = ClockSampler(local) if rank == 0 else None
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    if sampler:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    k1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    evals = 0
-    t_wall = time.perf_counter()
-    e0.record()
-    ev_list = []
-    for i in range(args.steps):
-        flush.zero_()                 # L2 flush between timed iterations (inside the timed region)
-        k0[i].record()
-        ev_list.append(step())
-        k1[i].record()
-    e1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    wall_ms = (time.perf_counter() - t_wall) * 1e3
-    clocks = sampler.stop() if sampler else None
-    ms = e0.elapsed_time(e1)
-    kernel_ms = sum(a.elapsed_time(b) for a, b in zip(k0, k1)) / args.steps
-    evals = sum(int(e.item()) for e in ev_list)
-    stats = torch.tensor([ms, float(evals), kernel_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        mx = stats.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = stats.clone()
-        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        ms, kernel_ms = float(mx[0]), float(mx[2])
-        total_evals = float(sm[1]) if "w" in wl else float(units) * args.steps
-    else:
-        total_evals = float(evals)
-    total_iters = total_evals * iters_per_eval
+    t = timed_run(run, args.steps, args.warmup, flush, sampler)
+    shard_check = run.check()
+    ms, total_evals, total_iters = t["ms"], t["total_evals"], t["total_iters"]
+    if not run.frame:
+        total_iters = float(run.units) * args.steps * iters_per_eval
+        total_evals = float(run.units) * args.steps
     value = total_iters / (ms * 1e-3) / 1e9
 
-    # ---- end-to-end through the C ABI with host buffers (every rank, its own frame)
+    # ---- end to end with HOST buffers
     e2e = None
-    if "w" in wl:
-        host_rgba = torch.zeros((wl["h"], wl["w"], 4), dtype=torch.uint8).pin_memory().numpy()
-        lp.render_host(cam, prm, seq, lights, n_lights, wl["w"], wl["h"], mode=args.mode, device=local, want_points=False, rgba=host_rgba)
-        if world > 1:
+    if run.frame:
+        w, h = wl["w"], wl["h"]
+        host_rgba = torch.zeros((h, w, 4), dtype=torch.uint8).pin_memory()
+        h2d = int(224 * n_lights + 224 + 56 + seq.nbytes)
+        if world == 1:
+            hr = host_rgba.numpy()
+            lp.render_host(cam, prm, seq, lights, n_lights, w, h, mode=args.mode, device=local, want_points=False, rgba=hr)
+            t0 = time.perf_counter()
+            e_evals = 0
+            for _ in range(args.steps):
+                e_evals += lp.render_host(cam, prm, seq, lights, n_lights, w, h, mode=args.mode, device=local, want_points=False, rgba=hr)[2]
+            dt = time.perf_counter() - t0
+            how = "lyap_render_host (C ABI, host buffers: H2D of lights + kernel + D2H of the frame + sync per call)"
+        else:
+            host_ev = torch.zeros(1, dtype=torch.int64).pin_memory()
+
+            def e2e_step():
+                d_l = api.upload_lights(lights, dev)                      # H2D of this step's inputs
+                run.d_lights = d_l
+                ev = run.step()                                           # zero + barrier + sharded render + barrier
+                host_ev.copy_(ev, non_blocking=True)
+                if rank == 0:
+                    host_rgba.copy_(run.p_rgba.view((h, w, 4), "|u1").tensor(), non_blocking=True)   # D2H of the assembled frame
+                torch.cuda.current_stream().synchronize()
+                return int(host_ev.item())
+            e2e_step()
             dist.barrier()
-        t0 = time.perf_counter()
-        e_evals = 0
-        for _ in range(args.steps):
-            _, _, e = lp.render_host(cam, prm, seq, lights, n_lights, wl["w"], wl["h"], mode=args.mode, device=local,
-                                     want_points=False, rgba=host_rgba)
-            e_evals += e
-        dt = time.perf_counter() - t0
-        t = torch.tensor([dt, float(e_evals)], dtype=torch.float64, device=dev)
+            t0 = time.perf_counter()
+            e_evals = 0
+            for _ in range(args.steps):
+                e_evals += e2e_step()
+            dist.barrier()
+            dt = time.perf_counter() - t0
+            how = ("peer-sharded render (dist.render_frame_sharded_peer: per step H2D of lights on every rank, zero + barrier, tile kernels "
+                   "storing into rank 0's frame over NVLink, barrier) + rank 0's D2H of the assembled frame into pinned memory")
+        tt = torch.tensor([dt, float(e_evals)], dtype=torch.float64, device=dev)
         if world > 1:
-            tm = t.clone()
+            tm = tt.clone()
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-            ts = t.clone()
+            ts = tt.clone()
             dist.all_reduce(ts, op=dist.ReduceOp.SUM)
             dt, e_evals = float(tm[0]), float(ts[1])
-        e2e = {"value": e_evals * iters_per_eval / dt / 1e9, "unit": "Giter/s",
-               "h2d_bytes_per_step": int(224 * n_lights + 224 + 56 + seq.nbytes),
-               "d2h_bytes_per_step": int(wl["w"] * wl["h"] * 4 + 8),
-               "ms_per_step": dt / args.steps * 1e3, "frames_per_s": args.steps * world / dt,
-               "api": "lyap_render_host (C ABI, host buffers: H2D of lights + kernel + D2H of the frame + sync per call)"}
+        e2e = {"value": e_evals * iters_per_eval / dt / 1e9, "unit": "Giter/s", "h2d_bytes_per_step": h2d * world,
+               "d2h_bytes_per_step": int(w * h * 4 + 8 * world), "ms_per_step": dt / args.steps * 1e3,
+               "frames_per_s": args.steps / dt, "api": how}
+    run.close()
 
-    if peer is not None:
-        peer.close()
+    # ---- the north-star's other multi-GPU configs in the same run (strong scaling, byte-checked)
+    sub = None
+    if not args.no_subrecords and args.workload == "frame1080":
+        sub = {}
+        sub["frame4k"] = sub_record("frame4k", args.mode if args.mode in ("exact", "fast") else "exact", 2, 1, rank, world, dev, flush)
+        sub["bake512_fast"] = sub_record("bake512", "fast", 5, 2, rank, world, dev, flush)
+        sub["bake512_exact"] = sub_record("bake512", "exact", 5, 2, rank, world, dev, flush)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
     # ---- roofline of the dominant kernel, from this run's own events and live peaks
-    sms = peaks["sm_count"]
-    if args.mode == "fast":
+    if args.mode in ("fast", "hybrid", "hybrid_host") and (args.mode == "fast" or prm.jitter == 0.0):
         fp32_per_iter = (2.0 * prm.settle + 4.0 * prm.accum) / iters_per_eval
         peak = peaks["ffma_lane_ops_per_s"] / fp32_per_iter / 1e9
         bound, note = "fp32", "FFMA-issue bound: %.3f FP32 lane-ops per iteration" % fp32_per_iter
+        if args.mode != "fast":
+            note += " (march samples, ~97.7 % of the evaluations; refinement and normals run on the parity evaluator)"
     else:
         mufu_per_iter = prm.accum / iters_per_eval
         peak = peaks["mufu_lane_ops_per_s"] / mufu_per_iter / 1e9
         bound, note = "sfu", "MUFU.LG2-issue bound: %.4f lg2 per iteration" % mufu_per_iter
     per_gpu_iters_per_step = total_iters / args.steps / world
-    achieved = per_gpu_iters_per_step / (kernel_ms * 1e-3) / 1e9
+    achieved = per_gpu_iters_per_step / (t["step_ms"] * 1e-3) / 1e9
     traffic_path = os.path.join(ROOT, "profiles", "traffic_%s_%s.json" % (args.workload, args.mode))
-    traffic = json.load(open(traffic_path)).get("dram_bytes_per_launch") if os.path.exists(traffic_path) else None
-    out_bytes = units * (40 if "w" in wl else 4) / world
+    traffic = json.load(open(traffic_path)).get("dram_bytes_per_launch") if (os.path.exists(traffic_path) and world == 1) else None
+    out_bytes = run.out_bytes / world          # every rank's launch writes its 1/N of the frame / volume
+    kernel = ("march_fast2_kernel + render_kernel" if args.mode.startswith("hybrid") and prm.jitter == 0.0 else
+              "render_fast2_kernel" if args.mode == "fast" else "render_kernel<%s>" % args.mode.replace("hybrid_host", "host").replace("hybrid", "exact"))
+    if not run.frame:
+        kernel = "bake_kernel<%s>" % args.mode
     roofline = {"bound": bound, "achieved": achieved, "peak": peak, "unit": "Giter/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "render_kernel<%s>" % args.mode if "w" in wl else "bake_kernel<%s>" % args.mode,
+                "traffic": traffic, "kernel": kernel,
                 "peak_source": "measured live by lyap_probe_peaks (register-only MUFU.LG2/FFMA loops on this GPU): "
-                               "%.2f T MUFU/s, %.2f T FFMA/s" % (peaks["mufu_lane_ops_per_s"] / 1e12, peaks["ffma_lane_ops_per_s"] / 1e12),
-                "note": note, "algorithmic_bytes_per_launch": out_bytes,
-                "hbm_gbs_sanity": out_bytes / (kernel_ms * 1e-3) / 1e9}
+                               "%.2f T MUFU/s, %.2f T FFMA/s; theoretical %d SMs x 16 resp. 128 lanes x clock"
+                               % (peaks["mufu_lane_ops_per_s"] / 1e12, peaks["ffma_lane_ops_per_s"] / 1e12, peaks["sm_count"]),
+                "frac_of_theoretical": None, "note": note, "algorithmic_bytes_per_launch": out_bytes,
+                "hbm_gbs_sanity": out_bytes / (t["step_ms"] * 1e-3) / 1e9}
+    clk = (t["clocks"] or {}).get("sm_mhz") or (t["clocks"] or {}).get("sm_max_mhz")
+    if clk:
+        lanes = 128.0 / ((2.0 * prm.settle + 4.0 * prm.accum) / iters_per_eval) if bound == "fp32" else 16.0 / (prm.accum / iters_per_eval)
+        roofline["frac_of_theoretical"] = achieved / (peaks["sm_count"] * lanes * clk * 1e6 / 1e9)
 
     cpu = None
-    if not args.no_cpu_baseline and "w" in wl and world == 1:
+    if not args.no_cpu_baseline and run.frame and world == 1:
         from oracle import Oracle   # the checker, timed as the reported CPU baseline only
         port = Oracle()
-        port.set_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+        port.set_threads(host_threads())
         rows = sample_rows(wl["h"], args.cpu_rows)
-        it, secs, _ = cpu_sample(port, port, wl, scene, rows)
+        it, secs, _ = cpu_sample(port, port, wl, run.scene, rows)
         cpu = {"value": it / secs / 1e9, "unit": "Giter/s", "cores": port.threads(), "kind": "port",
                "sample": f"{len(rows)} evenly spaced rows of the frame ({len(rows) * wl['w']} pixels), {secs:.1f} s"}
 
+    ref_cuda = None
+    if not args.no_reference_cuda and run.frame and world == 1:
+        try:
+            # its evaluation count is the exact-mode count (bit-identical march, tests/test_gpu_parity.py)
+            ev_exact = total_evals / args.steps if args.mode == "exact" else float(
+                lp.render(cam, prm, seq, lights, n_lights, wl["w"], wl["h"], mode="exact")[2].item())
+            ref_cuda = time_reference_cuda(wl, run.scene, ev_exact, 1)
+            if ref_cuda:
+                ref_cuda["speedup"] = ref_cuda["ms"] / t["ms_per_step"]
+        except Exception as exc:          # a missing checker must not take the headline down
+            ref_cuda = {"unavailable": repr(exc)}
+
+    n_kernels = 2 if (args.mode.startswith("hybrid") and prm.jitter == 0.0) else 1
     line = {
         "metric": "lyapunov_giga_iters_per_s", "value": value, "unit": "Giter/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak" if "w" in wl else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["what"] + (", one frame per GPU per step" if "w" in wl else ", z-slabs across GPUs"),
-                   "mode": args.mode, "sequence": wl["seq"], "settle": prm.settle, "accum": prm.accum,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["what"] + (", ONE frame per step: %dx%d tiles round-robin over the GPUs" % (TILE, TILE) if run.frame
+                                             else ", ONE volume per step: z-slabs across the GPUs"),
+                   "mode": args.mode, "sequence": wl["seq"], "settle": prm.settle, "accum": prm.accum, "jitter": prm.jitter,
                    "l2": "flushed between timed steps (256 MiB device write inside the timed region)",
                    "gather": ("none needed: every rank's kernel stores its shard directly into rank 0's buffer over NVLink "
-                              "(CUDA IPC peer mapping); stream sync + barrier per step inside the timed region") if world > 1 else "none"},
-        "frames_per_s": (args.steps * world / (ms * 1e-3)) if "w" in wl else None,
-        "evaluations_per_step": total_evals / args.steps, "wall_ms": wall_ms,
-        "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps * world,
-        "roofline": roofline, "cpu_baseline": cpu,
+                              "(CUDA IPC peer mapping); per step inside the timed region: zero of the shared point buffer + barrier, "
+                              "kernel, stream sync + barrier") if world > 1 else "none",
+                   "limiter_at_n_gpus": "the longest single ray (a strictly sequential chain of ~1.6e6 dependent FP32 steps, ~6.6 ms) and the "
+                                        "few rays per lane left at 1/N of a frame -- not a collective" if world > 1 else None},
+        "frames_per_s": (args.steps / (ms * 1e-3)) if run.frame else None,
+        "evaluations_per_step": total_evals / args.steps, "wall_ms": t["wall_ms"],
+        "clocks": t["clocks"], "e2e": e2e, "gpu_launches": n_kernels * args.steps * world,
+        "roofline": roofline, "cpu_baseline": cpu, "reference_cuda": ref_cuda, "shard_check": shard_check, "sub": sub,
     }
     print(json.dumps(line))
     if world > 1:

@@ -29,7 +29,7 @@ CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-I", os.path.jo
 
 CU = (["abi.cu", "kernels/misc.cu"] + [f"kernels/tu_{k}_{m}.cu" for k in ("render", "bake") for m in ("exact", "fast", "host")]
       + ["kernels/tu_march_exact.cu", "kernels/tu_march_host.cu"])
-CPP = ["host/scene.cpp", "host/imageio.cpp"]
+CPP = ["host/scene.cpp", "host/scenefile.cpp", "host/imageio.cpp"]
 APPS = ["lyap_render", "lyap_calculate"]
 BIN = os.path.join(PKG, "bin")
 

@@ -11,7 +11,7 @@ import os
 
 import numpy as np
 
-from .structs import MAX_LIGHTS, POINT_DTYPE, Cam, LightArray, Params
+from .structs import MAX_LIGHTS, POINT_DTYPE, Cam, LightArray, Params, Scene
 
 MODE_EXACT, MODE_FAST, MODE_HOST, MODE_HYBRID, MODE_HYBRID_HOST = 0, 1, 2, 3, 4
 MODES = {"exact": MODE_EXACT, "fast": MODE_FAST, "host": MODE_HOST, "hybrid": MODE_HYBRID, "hybrid_host": MODE_HYBRID_HOST}
@@ -72,6 +72,15 @@ def lib():
     L.lyap_write_raw.argtypes = [C.c_char_p, vp, u64]
     L.lyap_format_filename.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_ulong, u32, u32, C.c_char_p, vp, vp]
     L.lyap_probe_peaks.argtypes = [vp, vp, vp, vp]
+    L.lyap_scene_defaults.argtypes = [vp]
+    L.lyap_scene_defaults.restype = None
+    L.lyap_scene_parse.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_size_t]
+    L.lyap_scene_load.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_size_t]
+    L.lyap_scene_finalize.argtypes = [vp, u32, u32]
+    L.lyap_scene_finalize.restype = None
+    L.lyap_scene_format.argtypes = [vp, C.c_char_p, C.c_size_t]
+    L.lyap_scene_format.restype = C.c_size_t
+    L.lyap_scene_save.argtypes = [vp, C.c_char_p]
     L.lyap_host_workspace_release.restype = None
     L.lyap_peer_alloc.argtypes = [C.POINTER(vp), u64]
     L.lyap_peer_free.argtypes = [vp]
@@ -137,6 +146,50 @@ def campath_orbit(i, cam):
 
 def campath_frame(f, n_frames, cam):
     lib().lyap_campath_frame(f, n_frames, C.byref(cam))
+
+
+# ------------------------------------------------------------------ scene files
+def scene_defaults():
+    """params_init() as one lyap_scene (include/lyap/scene.h)."""
+    sc = Scene()
+    lib().lyap_scene_defaults(C.byref(sc))
+    return sc
+
+
+def scene_parse(text, scene=None):
+    """Apply `key = value` lines on top of `scene` (default: the params_init() scene)."""
+    sc = scene if scene is not None else scene_defaults()
+    err = C.create_string_buffer(256)
+    rc = lib().lyap_scene_parse(C.byref(sc), text.encode(), err, 256)
+    if rc != 0:
+        raise LyapError(f"scene: {err.value.decode()}")
+    return sc
+
+
+def scene_load(path):
+    sc = Scene()
+    err = C.create_string_buffer(256)
+    rc = lib().lyap_scene_load(C.byref(sc), str(path).encode(), err, 256)
+    if rc != 0:
+        raise LyapError(f"scene {path}: {err.value.decode() or lib().lyap_error_string(rc).decode()}")
+    return sc
+
+
+def scene_finalize(scene, width=0, height=0):
+    """Recompute the derived camera / light fields (the reference's update_scene())."""
+    lib().lyap_scene_finalize(C.byref(scene), width, height)
+    return scene
+
+
+def scene_format(scene):
+    n = lib().lyap_scene_format(C.byref(scene), None, 0)
+    buf = C.create_string_buffer(n + 1)
+    lib().lyap_scene_format(C.byref(scene), buf, n + 1)
+    return buf.value.decode()
+
+
+def scene_save(scene, path):
+    _check(lib().lyap_scene_save(C.byref(scene), str(path).encode()), "lyap_scene_save")
 
 
 def plan_period(seq, settle, accum):

@@ -3,8 +3,9 @@
 // with the volume size, sequence, mode and output name as run-time options instead of
 // compile-time constants.
 //
-//   lyap_calculate [-n 512] [-seq BCABA] [-settle 18] [-accum 1008] [-d 2.1]
+//   lyap_calculate [-scene file] [-n 512] [-seq BCABA] [-settle 18] [-accum 1008] [-d 2.1]
 //                  [-mode fast|exact|host] [-f16] [-device 0] [-o exps.raw]
+// (-scene: d, settle, accum and the sequence of a scene file, include/lyap/scene.h)
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -13,6 +14,7 @@
 #include <vector>
 
 #include "lyap/abi.h"
+#include "lyap/scene.h"
 
 static int mode_of(const char *s)
 {
@@ -27,7 +29,7 @@ int main(int argc, char **argv)
     lyap_cam cam;
     std::vector<lyap_light> lights(LYAP_MAX_LIGHTS);
     uint32_t n_lights = 0, iw = 0, ih = 0;
-    char seq_str[256];
+    char seq_str[LYAP_SCENE_SEQUENCE_CAP];
     lyap_params_init(&prm, &cam, lights.data(), &n_lights, seq_str, sizeof seq_str, &iw, &ih);
 
     unsigned n = 512;
@@ -36,7 +38,15 @@ int main(int argc, char **argv)
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         auto next = [&]() -> const char * { return i + 1 < argc ? argv[++i] : ""; };
-        if (a == "-n") n = (unsigned)atoi(next());
+        if (a == "-scene") {
+            static lyap_scene sc;
+            char err[256];
+            const char *path = next();
+            if (lyap_scene_load(&sc, path, err, sizeof err) != LYAP_OK) { fprintf(stderr, "%s: %s\n", path, err); return 2; }
+            prm = sc.prm;
+            snprintf(seq_str, sizeof seq_str, "%s", sc.sequence);
+        }
+        else if (a == "-n") n = (unsigned)atoi(next());
         else if (a == "-seq") snprintf(seq_str, sizeof seq_str, "%s", next());
         else if (a == "-settle") prm.settle = (uint32_t)atoi(next());
         else if (a == "-accum") prm.accum = (uint32_t)atoi(next());

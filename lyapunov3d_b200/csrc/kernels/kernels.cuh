@@ -431,8 +431,12 @@ __global__ void __launch_bounds__(kRenderThreads, 3) march_fast2_kernel(const __
         if (!any_fast && parked == 0) break;
 
         if (any_fast && parked < a.guard_batch) {
+            // a parked slot sits the fast pass out on the dummy point: its own sample may well be a
+            // zero-derivative one (NaN parks too), which would drag the warp through the fast
+            // evaluator's out-of-line safe loop on every pass until the parity pass comes
             float l[2];
-            exponent_fast2<P>(a.plan, st[0].Px, st[0].Py, st[0].Pz, st[1].Px, st[1].Py, st[1].Pz, a.prm.d, l[0], l[1]);
+            exponent_fast2<P>(a.plan, park0 ? 3.0f : st[0].Px, park0 ? 3.0f : st[0].Py, park0 ? 3.0f : st[0].Pz,
+                              park1 ? 3.0f : st[1].Px, park1 ? 3.0f : st[1].Py, park1 ? 3.0f : st[1].Pz, a.prm.d, l[0], l[1]);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 if (j == 0 ? fast0 : fast1) {

@@ -90,6 +90,13 @@ class Params(C.Structure):
     ]
 
 
+class Scene(C.Structure):
+    """lyap_scene (include/lyap/scene.h): the run-time parameter surface."""
+
+    _fields_ = [("prm", Params), ("_pad0", C.c_uint32 * 2), ("cam", CamLight), ("lights", LightArray), ("num_lights", C.c_uint32),
+                ("width", C.c_uint32), ("height", C.c_uint32), ("sequence", C.c_char * 1024)]
+
+
 class Point(C.Structure):
     """LyapPoint (reference structs.hpp:70-76); 36 bytes."""
 
@@ -111,6 +118,7 @@ assert CamLight.diffusePower.offset == 160 and CamLight.specularColor.offset == 
 assert CamLight.specularPower.offset == 192 and CamLight.specularHardness.offset == 196
 assert CamLight.chaosColor.offset == 208
 assert C.sizeof(Params) == 56 and C.sizeof(Point) == 36 and C.sizeof(RGBA) == 4
+assert Scene.cam.offset == 64 and Scene.lights.offset == 288 and Scene.num_lights.offset == 288 + 16 * 224
 
 # numpy views of the two bulk outputs
 POINT_DTYPE = np.dtype(

@@ -418,7 +418,7 @@ def _jitter_free_cases(golden, scene):
 def test_hybrid_mode_reproduces_its_parity_mode(golden, scene, hybrid, parity):
     """jitter == 0 -> march on the packed fast evaluator (guard-banded), refinement and
     normals on the parity evaluator.  P, N, l of every record and every pixel must be bit-identical
-    to the parity mode's, the evaluation count equal, the cloud sums a/c equal to 1e-5 relative."""
+    to the parity mode's, the evaluation count equal, the cloud sums a/c equal to 2e-3 absolute."""
     for name, cam, prm, lights, n, seq, w, h in _jitter_free_cases(golden, scene):
         want_rgba, want_pts, want_ev = lp.render(cam, prm, seq, lights, n, w, h, mode=parity)
         got_rgba, got_pts, got_ev = lp.render(cam, prm, seq, lights, n, w, h, mode=hybrid)
@@ -428,7 +428,8 @@ def test_hybrid_mode_reproduces_its_parity_mode(golden, scene, hybrid, parity):
         assert torch.equal(got_rgba, want_rgba), name
         assert int(got_ev.item()) == int(want_ev.item()), name
         for f in ("a", "c"):
-            assert np.allclose(a[f], b[f], rtol=1e-5, atol=1e-5, equal_nan=True), (name, f)
+            # sums of up to ~1.5e3 march exponents, each within ~1e-6 of the parity evaluator's
+            assert np.allclose(a[f], b[f], rtol=1e-5, atol=2e-3, equal_nan=True), (name, f, float(np.nanmax(np.abs(a[f] - b[f]))))
 
 
 def test_hybrid_host_mode_matches_reference_host_build(golden):
@@ -703,6 +704,56 @@ def test_headless_apps(tmp_path, scene):
     from PIL import Image
     png = [f for f in files if f.endswith(".png")][0]
     assert np.array_equal(np.asarray(Image.open(tmp_path / png).convert("RGB")), rgba.cpu().numpy()[..., :3])
+
+
+def test_lyap_render_from_scene_file_reproduces_golden_twolights_frame(tmp_path, golden):
+    """the whole parameter surface from a run-time file.  The golden two-light frame
+    of the unmodified reference (host-compiled) -- second light, chaos tint, light poses, nothing of
+    which the command-line flags can express -- reproduced byte for byte by `lyap_render -scene`,
+    and the dumped effective scene reloads to the same inputs."""
+    import os
+    import subprocess
+    from lyapunov3d_b200.structs import Scene, struct_bytes
+    cam, prm, lights, n_lights, seq_s, want_rgba, want_pts = frame_inputs(golden["frames"], "twolights_32")
+    assert n_lights == 2
+    sc = Scene()
+    sc.prm, sc.cam, sc.num_lights, sc.width, sc.height, sc.sequence = clone(prm), clone(cam), n_lights, 32, 32, seq_s.encode()
+    for k in range(16):
+        sc.lights[k] = lights[k]
+    scene_path = tmp_path / "twolights.scene"
+    api.scene_save(sc, scene_path)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "lyapunov3d_b200", "bin", "lyap_render")
+    r = subprocess.run([exe, "-scene", str(scene_path), "-mode", "host", "-ppm", "-points", "-dump-scene", "-dir", str(tmp_path)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    files = sorted(os.listdir(tmp_path))
+    ppm = [f for f in files if f.endswith(".ppm")][0]
+    vals = np.array(open(tmp_path / ppm).read().split()[4:], dtype=np.int64).reshape(32, 32, 3)
+    lib_rgba = lp.render(cam, prm, lp.scene_convert_sequence(seq_s), lights, n_lights, 32, 32, mode="host")[0].cpu().numpy()
+    assert np.array_equal(vals, lib_rgba[..., :3])                                 # the file carries the whole scene, bit for bit
+    assert frac_within(vals, want_rgba[..., :3], PIXEL_TOL) >= PIXEL_FRAC          # and that is the golden frame
+    assert (vals == want_rgba[..., :3]).all(-1).mean() >= PIXEL_FRAC               # (pow is CUDA's, not glibc's: in practice identical)
+    raw = np.fromfile(tmp_path / [f for f in files if f.startswith("Points_")][0], POINT_DTYPE).reshape(32, 32)
+    assert point_rows_equal(raw, want_pts).all()
+    dumped = api.scene_finalize(api.scene_load(tmp_path / [f for f in files if f.startswith("Render_") and f.endswith(".scene")][0]))
+    assert struct_bytes(dumped.cam) == struct_bytes(cam) and struct_bytes(dumped.prm) == struct_bytes(prm)
+    # single-key overrides on top of the file: the jitter-free variant equals the library call
+    r = subprocess.run([exe, "-scene", str(scene_path), "-set", "jitter=0", "-set", "light1.chaosColor=0 0 0 0", "-mode", "hybrid_host",
+                        "-ppm", "-dir", str(tmp_path / "b")], capture_output=True, text=True)
+    assert r.returncode != 0                                                        # the directory does not exist: an error, not a crash
+    os.makedirs(tmp_path / "b")
+    r = subprocess.run([exe, "-scene", str(scene_path), "-set", "jitter=0", "-set", "light1.chaosColor=0 0 0 0", "-mode", "hybrid_host",
+                        "-ppm", "-dir", str(tmp_path / "b")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    p0 = clone(prm)
+    p0.jitter = 0.0
+    l0 = clone(lights)
+    l0[1].chaosColor.r = l0[1].chaosColor.g = l0[1].chaosColor.b = l0[1].chaosColor.a = 0.0
+    want = lp.render(cam, p0, lp.scene_convert_sequence(seq_s), l0, 2, 32, 32, mode="host")[0].cpu().numpy()
+    ppm = [f for f in os.listdir(tmp_path / "b") if f.endswith(".ppm")][0]
+    vals = np.array(open(tmp_path / "b" / ppm).read().split()[4:], dtype=np.int64).reshape(32, 32, 3)
+    assert np.array_equal(vals, want[..., :3])
 
 
 def test_every_period_instantiation_and_odd_iteration_counts(oracle, scene):
