@@ -69,7 +69,7 @@ const char *lyap_error_string(int code);
  * the per-step-select exponent loop instead of a period instantiation),
  * "emulate_ref_nvcc_normals" (test knob: reproduce the normals the reference's CUDA
  * build produces under nvcc 12.9, where ls[] aliases lyap4d's abcd[]),
- * "hybrid_guard_batch" (parked lanes per warp that trigger a parity pass; 0 = default),
+ * "hybrid_guard_batch" (parked lanes per warp that trigger a parity pass; 0 = default = 1),
  * "hybrid_guard_percent" (test knob: guard band width in % of the derived bound).
  * The knobs are process-global and read at launch time: set them before launching from
  * several threads, not concurrently with launches. */
@@ -139,6 +139,31 @@ uint64_t lyap_tile_count(uint32_t width, uint32_t height, uint32_t tile, uint32_
 /* Rank 0: place a rank's compact buffer (elem_size bytes per item) into the full image. */
 int lyap_scatter_tiles(void *d_image, const void *d_compact, uint32_t elem_size, uint32_t width, uint32_t height,
                        uint32_t tile, uint32_t rank, uint32_t world, void *stream);
+
+/* ----------------------------------------------------------------------------
+ * Volume-assisted rendering (beyond the reference).  A volume baked by
+ * lyap_bake with the SAME sequence / d / settle / accum classifies the cells of its n^3 grid
+ * (n a cube edge, samples at 4i/n); march samples that fall into a SAFE cell are stepped over
+ * without evaluating the exponent.  Hybrid modes only, and only when prm->jitter == 0 (otherwise the
+ * call renders exactly like lyap_render_tiles).  The ray positions are unchanged, so hit point,
+ * normal, exponent and pixel equal the non-assisted frame's wherever no surface crossing hides inside
+ * a "safe" neighbourhood; the cloud sums a / c take the baked value of each skipped sample's cell.
+ *
+ * lyap_assist_build: cell (i,j,k) is SAFE when every volume sample of the neighbourhood
+ * i-dilate .. i+1+dilate (all three axes) exists, is finite, and lies strictly between
+ * max(opaqueThreshold, nearThreshold) + margin and `upper` (pass +inf for no upper bound; e.g. 0
+ * keeps the march exact inside chaotic regions, whose thin stable windows no grid resolves).
+ * d_safe_bits holds lyap_assist_bits_bytes(n) bytes: one bit per cell, x fastest.
+ * d_skipped: optional device counter, += number of samples stepped over.
+ * ------------------------------------------------------------------------- */
+uint64_t lyap_assist_bits_bytes(uint32_t n);
+int lyap_assist_build(uint32_t *d_safe_bits, const void *d_volume, int dtype, uint32_t n, const lyap_params *prm,
+                      float margin, float upper, uint32_t dilate, void *stream);
+int lyap_render_assisted(lyap_rgba *d_rgba, lyap_point *d_points, const lyap_cam *cam, const lyap_params *prm,
+                         const int32_t *seq, const lyap_light *d_lights, uint32_t num_lights,
+                         uint32_t width, uint32_t height, uint32_t tile, uint32_t rank, uint32_t world, int compact, int mode,
+                         const void *d_volume, int dtype, uint32_t n, const uint32_t *d_safe_bits,
+                         unsigned long long *d_evals, unsigned long long *d_skipped, void *stream);
 
 /* Re-shade a stored LyapPoint buffer without marching (lights/camera edits). */
 int lyap_shade_points(lyap_rgba *d_rgba, const lyap_point *d_points, const lyap_cam *cam,

@@ -60,6 +60,10 @@ def lib():
     L.lyap_tile_count.restype = u64
     L.lyap_tile_count.argtypes = [u32, u32, u32, u32, u32]
     L.lyap_scatter_tiles.argtypes = [vp, vp, u32, u32, u32, u32, u32, u32, vp]
+    L.lyap_assist_bits_bytes.restype = u64
+    L.lyap_assist_bits_bytes.argtypes = [u32]
+    L.lyap_assist_build.argtypes = [vp, vp, i32, u32, vp, C.c_float, C.c_float, u32, vp]
+    L.lyap_render_assisted.argtypes = [vp, vp, vp, vp, vp, vp, u32, u32, u32, u32, u32, u32, i32, i32, vp, i32, u32, vp, vp, vp, vp]
     L.lyap_shade_points.argtypes = [vp, vp, vp, vp, u32, u64, i32, vp]
     L.lyap_bake.argtypes = [vp, i32, vp, vp, u32, u32, u32, u32, u32, i32, vp]
     L.lyap_exponent_points.argtypes = [vp, vp, u64, vp, vp, i32, vp]
@@ -266,6 +270,41 @@ def render(cam, prm, seq, lights, num_lights, width, height, mode="exact", point
                                  _mode(mode), ev_ptr, _stream_ptr(torch))
     _check(rc, "lyap_render")
     return rgba, points, evals
+
+
+def assist_build(volume, prm, margin=0.25, upper=float("inf"), dilate=1):
+    """Classify the cells of a baked cubic volume (float32 or float16 CUDA tensor [n,n,n]) for the
+    volume-assisted march.  Returns the bit mask (int32 CUDA tensor)."""
+    torch = _torch()
+    n = volume.shape[0]
+    assert volume.is_contiguous() and tuple(volume.shape) == (n, n, n)
+    bits = torch.zeros(lib().lyap_assist_bits_bytes(n) // 4, dtype=torch.int32, device=volume.device)
+    _check(lib().lyap_assist_build(bits.data_ptr(), volume.data_ptr(), F16 if volume.dtype == torch.float16 else F32, n, C.byref(prm),
+                                   float(margin), float(upper), int(dilate), _stream_ptr(torch)), "lyap_assist_build")
+    return bits
+
+
+def render_assisted(cam, prm, seq, lights, num_lights, width, height, volume, safe_bits, mode="hybrid", points=None, rgba=None,
+                    tile=8, rank=0, world=1, compact=False):
+    """lyap_render_assisted: the hybrid render with march samples in safe cells stepped over.
+    Returns (rgba, points, evals, skipped)."""
+    torch = _torch()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    seq = np.ascontiguousarray(seq, np.int32)
+    d_lights = lights if hasattr(lights, "data_ptr") else upload_lights(lights, dev)
+    n_out = tile_count(width, height, tile, rank, world) if compact else width * height
+    shape = (n_out,) if compact else (height, width)
+    if points is None:
+        points = torch.zeros(shape + (36,), dtype=torch.uint8, device=dev)
+    if rgba is None:
+        rgba = torch.zeros(shape + (4,), dtype=torch.uint8, device=dev)
+    evals = torch.zeros(1, dtype=torch.int64, device=dev)
+    skipped = torch.zeros(1, dtype=torch.int64, device=dev)
+    _check(lib().lyap_render_assisted(rgba.data_ptr(), points.data_ptr(), C.byref(cam), C.byref(prm), seq.ctypes.data, d_lights.data_ptr(),
+                                      num_lights, width, height, tile, rank, world, int(compact), _mode(mode), volume.data_ptr(),
+                                      F16 if volume.dtype == torch.float16 else F32, volume.shape[0], safe_bits.data_ptr(),
+                                      evals.data_ptr(), skipped.data_ptr(), _stream_ptr(torch)), "lyap_render_assisted")
+    return rgba, points, evals, skipped
 
 
 def scatter_tiles(image, compact, width, height, tile, rank, world):

@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <string>
 #include <vector>
 
 #include "kernels/launch.hpp"
@@ -233,6 +234,30 @@ int lyap_set_option(const char *key, long value)
     return LYAP_OK;
 }
 
+// LYAP_OPTIONS="key=value,key=value" in the environment applies lyap_set_option() when the library
+// is loaded: the knobs of a program that links the library but does not call lyap_set_option itself
+// (the patched reference programs of integration/).
+namespace {
+struct EnvOptions {
+    EnvOptions()
+    {
+        const char *env = getenv("LYAP_OPTIONS");
+        if (!env) return;
+        std::string s(env);
+        size_t pos = 0;
+        while (pos < s.size()) {
+            size_t end = s.find(',', pos);
+            if (end == std::string::npos) end = s.size();
+            const std::string kv = s.substr(pos, end - pos);
+            const size_t eq = kv.find('=');
+            if (eq != std::string::npos && lyap_set_option(kv.substr(0, eq).c_str(), atol(kv.c_str() + eq + 1)) != LYAP_OK)
+                fprintf(stderr, "liblyap_b200: unknown option in LYAP_OPTIONS: %s\n", kv.c_str());
+            pos = end + 1;
+        }
+    }
+} g_env_options;
+} // namespace
+
 /* Which period instantiation a sequence would run on (0 = generic loop, -1 = invalid). */
 int lyap_plan_period(const int32_t *seq, uint32_t settle, uint32_t accum)
 {
@@ -265,10 +290,19 @@ uint64_t lyap_tile_count(uint32_t width, uint32_t height, uint32_t tile, uint32_
     return mine * tile * tile;
 }
 
-int lyap_render_tiles(lyap_rgba *d_rgba, lyap_point *d_points, const lyap_cam *cam, const lyap_params *prm,
-                      const int32_t *seq, const lyap_light *d_lights, uint32_t num_lights,
-                      uint32_t width, uint32_t height, uint32_t tile, uint32_t rank, uint32_t world,
-                      int compact, int mode, unsigned long long *d_evals, void *stream)
+namespace {
+struct Assist {
+    const void *vol;
+    int dtype;
+    uint32_t n;
+    const uint32_t *bits;
+    unsigned long long *skipped;
+};
+
+int render_impl(lyap_rgba *d_rgba, lyap_point *d_points, const lyap_cam *cam, const lyap_params *prm,
+                const int32_t *seq, const lyap_light *d_lights, uint32_t num_lights,
+                uint32_t width, uint32_t height, uint32_t tile, uint32_t rank, uint32_t world,
+                int compact, int mode, unsigned long long *d_evals, void *stream, const Assist *assist)
 {
     if (!d_rgba || !d_points || !cam || !prm || !valid_mode(mode) || !width || !height || !tile || tile > LYAP_MAX_TILE || !world || rank >= world)
         return LYAP_ERR_BAD_ARGUMENT;
@@ -307,6 +341,11 @@ int lyap_render_tiles(lyap_rgba *d_rgba, lyap_point *d_points, const lyap_cam *c
     if ((e = cudaMemsetAsync(a.queue, 0, sizeof(unsigned long long), s)) != cudaSuccess) return (int)e;
     a.worklist = nullptr;
     a.work_count = nullptr;
+    a.safe_bits = nullptr;
+    a.assist_vol = nullptr;
+    a.assist_n = a.assist_f16 = 0;
+    a.assist_scale = 0.0f;
+    a.skipped = nullptr;
 
     // Hybrid modes: with jitter the march exponents feed the jitter PRNG (kernel.cu:334-347) and
     // every sample must be the parity evaluator's, so the call is the parity mode itself.
@@ -318,7 +357,15 @@ int lyap_render_tiles(lyap_rgba *d_rgba, lyap_point *d_points, const lyap_cam *c
         a.guard[1] = (float)(scale * guard_half_width(prm->chaosThreshold, prm->accum));
         a.guard[2] = (float)(scale * guard_half_width(prm->nearThreshold, prm->accum));
         const long gb = g_guard_batch.load();
-        a.guard_batch = gb > 0 ? (uint32_t)(gb > 32 ? 32 : gb) : (host ? 8u : 4u);
+        a.guard_batch = gb > 0 ? (uint32_t)(gb > 32 ? 32 : gb) : 1u;
+        if (assist) {
+            a.safe_bits = assist->bits;
+            a.assist_vol = assist->vol;
+            a.assist_n = assist->n;
+            a.assist_f16 = assist->dtype == LYAP_F16;
+            a.assist_scale = (float)assist->n * 0.25f;
+            a.skipped = assist->skipped;
+        }
         // [count, padded to 16 bytes][work list]: stream-ordered, lives until the second launch is done
         unsigned char *mem = nullptr;
         if ((e = cudaMallocAsync(&mem, 16 + a.n_items * sizeof(uint32_t), s)) != cudaSuccess) return (int)e;
@@ -374,6 +421,53 @@ int lyap_render_tiles(lyap_rgba *d_rgba, lyap_point *d_points, const lyap_cam *c
                 [&] { return launch_render_fast(P, a, (unsigned)grid, s); },
                 [&] { return launch_render_host(P, a, (unsigned)grid, s); });
     return (int)e;
+}
+
+} // namespace
+
+int lyap_render_tiles(lyap_rgba *d_rgba, lyap_point *d_points, const lyap_cam *cam, const lyap_params *prm,
+                      const int32_t *seq, const lyap_light *d_lights, uint32_t num_lights,
+                      uint32_t width, uint32_t height, uint32_t tile, uint32_t rank, uint32_t world,
+                      int compact, int mode, unsigned long long *d_evals, void *stream)
+{
+    return render_impl(d_rgba, d_points, cam, prm, seq, d_lights, num_lights, width, height, tile, rank, world, compact, mode,
+                       d_evals, stream, nullptr);
+}
+
+uint64_t lyap_assist_bits_bytes(uint32_t n) { return (((uint64_t)n * n * n + 31) / 32) * 4; }
+
+int lyap_assist_build(uint32_t *d_safe_bits, const void *d_volume, int dtype, uint32_t n, const lyap_params *prm,
+                      float margin, float upper, uint32_t dilate, void *stream)
+{
+    if (!d_safe_bits || !d_volume || !prm || n < 2 || n > 2048 || dilate > 8 || (dtype != LYAP_F32 && dtype != LYAP_F16) || !(margin >= 0.0f))
+        return LYAP_ERR_BAD_ARGUMENT;
+    DeviceScratch *sc = nullptr;
+    cudaError_t e = scratch_for_current_device(&sc);
+    if (e != cudaSuccess) return (int)e;
+    AssistBuildArgs a;
+    a.bits = d_safe_bits;
+    a.vol = d_volume;
+    a.f16 = dtype == LYAP_F16;
+    a.n = n;
+    a.dilate = dilate;
+    // a skipped sample must neither end the march (l > opaque) nor switch the step (l > near)
+    const float floor_thr = prm->opaqueThreshold > prm->nearThreshold ? prm->opaqueThreshold : prm->nearThreshold;
+    a.lo = floor_thr + margin;
+    a.hi = upper;
+    return (int)launch_assist_build(a, (unsigned)sc->sm_count * 8u, (cudaStream_t)stream);
+}
+
+int lyap_render_assisted(lyap_rgba *d_rgba, lyap_point *d_points, const lyap_cam *cam, const lyap_params *prm,
+                         const int32_t *seq, const lyap_light *d_lights, uint32_t num_lights,
+                         uint32_t width, uint32_t height, uint32_t tile, uint32_t rank, uint32_t world, int compact, int mode,
+                         const void *d_volume, int dtype, uint32_t n, const uint32_t *d_safe_bits,
+                         unsigned long long *d_evals, unsigned long long *d_skipped, void *stream)
+{
+    if (!hybrid_mode(mode) || !d_volume || !d_safe_bits || n < 2 || n > 2048 || (dtype != LYAP_F32 && dtype != LYAP_F16))
+        return LYAP_ERR_BAD_ARGUMENT;
+    const Assist as{d_volume, dtype, n, d_safe_bits, d_skipped};
+    return render_impl(d_rgba, d_points, cam, prm, seq, d_lights, num_lights, width, height, tile, rank, world, compact, mode,
+                       d_evals, stream, &as);
 }
 
 int lyap_render(lyap_rgba *d_rgba, lyap_point *d_points, const lyap_cam *cam, const lyap_params *prm,

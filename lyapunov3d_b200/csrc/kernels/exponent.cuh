@@ -144,7 +144,7 @@ struct Accum<kHost> {
     {
         logistic_step<kHost>(r, v);
         const float d = __fmaf_rn(-(r + r), v, r);
-        l = __fadd_rn(l, glibc_logf_careful(fabsf(d), ctx));
+        l = __fadd_rn(l, glibc_logf_careful(fabsf(d)));
     }
     __device__ __forceinline__ void renorm() {}
     __device__ __forceinline__ float finish(const SeqPlan &sp, float, float, float, float, float)

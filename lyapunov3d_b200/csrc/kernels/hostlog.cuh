@@ -16,11 +16,7 @@
 // source.  With or without FMA contraction of the double expressions the float
 // result is the same except when y lies within ~1e-16 of a rounding boundary:
 // 0 differences against the installed libm over 3e8 inputs for both forms, so the
-// fused form (7 FP64 ops) is used here.
-//
-// int->double and float->double conversions are done with integer bit
-// construction instead of F2F/I2F (XU pipe); only the final double->float
-// rounding uses a conversion instruction.
+// fused form is used here.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -37,13 +33,32 @@ static __device__ const double kLogfTab[32] = {
     0x1.b2036576afce6p-1, 0x1.526e57720db08p-3,  0x1.9c2d163a1aa2dp-1, 0x1.bc2860d224770p-3,
     0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2,  0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2};
 
-// Per-block copy of the table: the index differs per lane, which shared memory serves at
-// full rate and the constant cache would serialise.
-static __shared__ double2 s_logf_tab[16];
+// Hot-loop form.  glibc splits x = 2^k * z and looks (invc, logc) up by the top four mantissa bits of
+// z; here ONE shared-memory table, indexed by the ten bits (k mod 64, i) of the shifted bit pattern,
+// holds the pair already combined with k:
+//     invc' = invc[i] * 2^-k      (a power-of-two scale: exact)     so  z*invc - 1 == x*invc' - 1
+//     y0    = logc[i] + k*ln2     (the same fused double expression the scalar form evaluates)
+// which removes the reduction of x to z, the int->double conversion of k and two of the eight FP64
+// operations from every step: r = fma((double)x, invc', -1); y = (A0 r^2 + (A1 r + A2)) r^2 + (y0 + r)
+// -- bit for bit the value of the scalar form for every x with k in [kLogfKmin, kLogfKmin + 63]
+// (2^-60 <= x < 2^4, roughly).  Anything else -- zero, subnormals, infinities, NaN, huge or tiny
+// magnitudes -- indexes a wrong entry, is caught by one unsigned range compare, and the caller redoes
+// the whole sample with the careful form (glibc's special cases included).
+//
+// A per-block copy in shared memory: the index differs per lane, which shared memory serves at full
+// rate and the constant cache would serialise.
+constexpr int kLogfKmin = -60;
+static __shared__ double2 s_logf_tab[1024];
 
 __device__ __forceinline__ void hostlog_init()
 {
-    if (threadIdx.x < 16) s_logf_tab[threadIdx.x] = make_double2(kLogfTab[2 * threadIdx.x], kLogfTab[2 * threadIdx.x + 1]);
+    for (unsigned e = threadIdx.x; e < 1024; e += blockDim.x) {
+        const int i = (int)(e & 15u);
+        const int k = (int)(((e >> 4) + (unsigned)(-kLogfKmin)) & 63u) + kLogfKmin;   // the k in range with k mod 64 == e >> 4
+        const double scale = __hiloint2double((1023 - k) << 20, 0);                   // 2^-k
+        s_logf_tab[e] = make_double2(__dmul_rn(kLogfTab[2 * i], scale),
+                                     __fma_rn((double)k, 0x1.62e42fefa39efp-1, kLogfTab[2 * i + 1]));
+    }
     __syncthreads();
 }
 
@@ -54,15 +69,11 @@ static __device__ const double kLogfPoly[5] = {-0x1.00ea348b88334p-2, 0x1.5575b0
                                                0x1.62e42fefa39efp-1, 4503601774854144.0 /* 2^52 + 2^31 */};
 
 struct LogfCtx {
-    double a0, a1, a2, ln2, magic;
-    uint32_t tab;   // shared-window address of s_logf_tab
+    double a0, a1, a2;
     __device__ __forceinline__ void init()
     {
         const volatile double *p = kLogfPoly;
-        a0 = p[0]; a1 = p[1]; a2 = p[2]; ln2 = p[3]; magic = p[4];
-        unsigned long long a;
-        asm volatile("cvta.to.shared.u64 %0, %1;" : "=l"(a) : "l"(s_logf_tab));
-        tab = (uint32_t)a;
+        a0 = p[0]; a1 = p[1]; a2 = p[2];
     }
 };
 
@@ -77,30 +88,27 @@ static __device__ __noinline__ unsigned long long glibc_logf_special(uint32_t ix
     return __float_as_uint(__fmul_rn(__uint_as_float(ix), 8388608.0f)) - (23u << 23);   // subnormal * 2^23 (exact)
 }
 
-// The main path for a normal positive x given as its bit pattern.
-__device__ __forceinline__ float glibc_logf_bits(uint32_t ix, const LogfCtx &c)
+// The scalar form for a normal positive x given as its bit pattern: glibc's own sequence of operations
+// (rare path: the careful redo of a sample, and shading).
+__device__ __forceinline__ float glibc_logf_bits(uint32_t ix)
 {
     const uint32_t tmp = ix - 0x3f330000u;
-    const uint32_t i16 = (tmp >> 15) & 0xf0u;          // table index * 16 bytes
+    const uint32_t i = (tmp >> 19) & 15u;
     const int k = (int)tmp >> 23;
     const uint32_t iz = ix - (tmp & 0xff800000u);
-    double invc, logc;
-    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(invc), "=d"(logc) : "r"(c.tab + i16));
-    // z = (double)asfloat(iz): iz is a normal float in [0.699, 1.399)
-    const double z = __hiloint2double((int)((iz >> 3) + 0x38000000u), (int)(iz << 29));
-    // (double)k without I2F: 2^52 + 2^31 + k is exact in the low word
-    const double kd = __dsub_rn(__hiloint2double(0x43300000, (int)((uint32_t)k ^ 0x80000000u)), c.magic);
+    const double invc = kLogfTab[2 * i], logc = kLogfTab[2 * i + 1];
+    const double z = (double)__uint_as_float(iz);
     const double r = __fma_rn(z, invc, -1.0);
-    const double y0 = __fma_rn(kd, c.ln2, logc);
+    const double y0 = __fma_rn((double)k, kLogfPoly[3], logc);
     const double r2 = __dmul_rn(r, r);
-    double y = __fma_rn(c.a1, r, c.a2);
-    y = __fma_rn(c.a0, r2, y);
+    double y = __fma_rn(kLogfPoly[1], r, kLogfPoly[2]);
+    y = __fma_rn(kLogfPoly[0], r2, y);
     y = __fma_rn(y, r2, __dadd_rn(y0, r));
     return __double2float_rn(y);
 }
 
 // |x| with full glibc semantics (any input).
-__device__ __forceinline__ float glibc_logf_careful(float x, const LogfCtx &c)
+static __device__ __noinline__ float glibc_logf_careful(float x)
 {
     uint32_t ix = __float_as_uint(x);
     if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {
@@ -108,25 +116,32 @@ __device__ __forceinline__ float glibc_logf_careful(float x, const LogfCtx &c)
         if (s >> 32) return __uint_as_float((uint32_t)s);
         ix = (uint32_t)s;
     }
-    return glibc_logf_bits(ix, c);
+    return glibc_logf_bits(ix);
 }
 
-// Speculative form for the hot loop: evaluates the main path on |x| whatever it is and records
-// in `odd` whether x was one of the rare inputs (0, subnormal, inf, nan); the caller redoes the
-// whole sample with glibc_logf_careful when the flag comes back set.
+// Speculative form for the hot loop: evaluates the merged-table path on |x| whatever it is and records
+// in `odd` whether x fell outside the table's range (0, subnormal, inf, nan, |x| < ~2^-60 or >= ~2^4);
+// the caller redoes the whole sample with glibc_logf_careful when the flag comes back set.
+// Per step: 1 LDS.128, 6 FP64 ops, 2 conversions, 4 integer ops.
 __device__ __forceinline__ float glibc_logf_speculative(float x, const LogfCtx &c, bool &odd)
 {
-    const uint32_t ix = __float_as_uint(x) & 0x7fffffffu;
-    odd = odd || (ix - 0x00800000u >= 0x7f800000u - 0x00800000u);
-    return glibc_logf_bits(ix, c);
+    // the sign bit of x falls out of the index mask, so |x| need not be formed for the lookup
+    const uint32_t tmp = __float_as_uint(x) - 0x3f330000u;
+    const double2 e = *reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(s_logf_tab) + ((tmp >> 15) & 0x3ff0u));
+    const double xd = (double)fabsf(x);
+    const double r = __fma_rn(xd, e.x, -1.0);
+    const double r2 = __dmul_rn(r, r);
+    // Range check for free: with the right table entry |r| < 2^-4.5; with k off by a multiple of 64
+    // (or x zero / subnormal / inf / nan) r is -1, huge or NaN.  r^2 is non-negative, so one unsigned
+    // compare of its high word against 2^-4 catches them all.
+    odd = odd || ((uint32_t)__double2hiint(r2) >= 0x3fb00000u);
+    double y = __fma_rn(c.a1, r, c.a2);
+    y = __fma_rn(c.a0, r2, y);
+    y = __fma_rn(y, r2, __dadd_rn(e.y, r));
+    return __double2float_rn(y);
 }
 
 // Single-lane variant for divergent callers (shading).
-__device__ __forceinline__ float glibc_logf_lane(float x)
-{
-    LogfCtx c;
-    c.init();
-    return glibc_logf_careful(x, c);
-}
+__device__ __forceinline__ float glibc_logf_lane(float x) { return glibc_logf_careful(x); }
 
 } // namespace lyap

@@ -154,6 +154,15 @@ struct RenderArgs {
     unsigned long long *work_count;
     float guard[3];                    // half-width of the guard band around opaque / chaos / near threshold
     uint32_t guard_batch;              // parked lanes per warp that trigger a parity-evaluator pass
+    // volume-assisted march: a baked exponent volume classifies the cells of its grid;
+    // march samples that fall into a cell whose whole neighbourhood is safely transparent are not
+    // evaluated -- the ray just steps on (same positions, same arithmetic) and the cloud sums take the
+    // cell's baked value.  Null `safe_bits` = plain hybrid march.
+    const uint32_t *safe_bits;         // one bit per cell of the n^3 grid, x fastest
+    const void *assist_vol;            // the baked volume the bits were built from (float or __half)
+    uint32_t assist_n, assist_f16;
+    float assist_scale;                // n / 4: sample coordinate -> cell index
+    unsigned long long *skipped;       // optional: += skipped samples
 };
 
 constexpr int kRenderThreads = 128;
@@ -363,7 +372,7 @@ __global__ void __launch_bounds__(kRenderThreads, 3) march_fast2_kernel(const __
         st[j].Px = st[j].Py = st[j].Pz = 3.0f;   // harmless dummy point for idle slots
     }
     bool drained = false;
-    unsigned long long evals = 0;
+    unsigned long long evals = 0, skipped = 0;
 
     auto out_of = [&](uint32_t item) {
         uint32_t px, py;
@@ -376,7 +385,26 @@ __global__ void __launch_bounds__(kRenderThreads, 3) march_fast2_kernel(const __
     };
     // consume one march exponent of slot s (fast one outside the guard bands, or the parity one)
     auto consume = [&](MarchState &s, float l) {
-        const RayEvent ev = march_consume<A>(s, l, a.prm);
+        RayEvent ev = march_consume<A>(s, l, a.prm);
+        if (ev == kContinue && a.safe_bits) {
+            // volume assist: step over samples in safely transparent cells without evaluating them.
+            // Only in the far-step state: a safe cell's exponents are above the near threshold, so an
+            // evaluated sample could only ever switch near -> far there, never the other way.
+            while (ev == kContinue && !s.near) {
+                const float fx = s.Px * a.assist_scale, fy = s.Py * a.assist_scale, fz = s.Pz * a.assist_scale;
+                const int ix = __float2int_rd(fx), iy = __float2int_rd(fy), iz = __float2int_rd(fz);
+                const int n = (int)a.assist_n;
+                if (!(ix >= 0 && ix < n && iy >= 0 && iy < n && iz >= 0 && iz < n)) break;    // NaN lands here too
+                const uint32_t cell = (uint32_t)ix + a.assist_n * ((uint32_t)iy + a.assist_n * (uint32_t)iz);
+                if (!((__ldg(a.safe_bits + (cell >> 5)) >> (cell & 31u)) & 1u)) break;
+                const float lv = a.assist_f16 ? __half2float(__ldg(reinterpret_cast<const __half *>(a.assist_vol) + cell))
+                                              : __ldg(reinterpret_cast<const float *>(a.assist_vol) + cell);
+                march_account<A>(s, lv, a.prm);     // cloud sums from the baked value; cannot end the march or switch the step
+                s.l = lv;
+                ++skipped;
+                ev = march_step<A>(s, a.prm);
+            }
+        }
         if (ev == kContinue) return;
         const uint32_t out = out_of(s.item);
         if (ev == kMiss) {
@@ -459,6 +487,11 @@ __global__ void __launch_bounds__(kRenderThreads, 3) march_fast2_kernel(const __
         for (int o = 16; o > 0; o >>= 1) evals += __shfl_xor_sync(full, evals, o);
         if (lane == 0) atomicAdd(a.evals, evals);
     }
+    if (a.skipped) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) skipped += __shfl_xor_sync(full, skipped, o);
+        if (lane == 0) atomicAdd(a.skipped, skipped);
+    }
 }
 
 // Shade-only pass over stored points (no marching): one thread per point.
@@ -480,6 +513,17 @@ __global__ void __launch_bounds__(256) shade_kernel(const __grid_constant__ Shad
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.count; i += stride)
         reinterpret_cast<uint32_t *>(a.rgba)[i] = shade_pixel<A>(a.points[i], a.cam, a.lights, a.n_lights);
 }
+
+// Classify the cells of a baked volume for the volume-assisted march: cell (i,j,k) spans the samples
+// i..i+1 on each axis; it is SAFE when every sample of the neighbourhood i-dilate .. i+1+dilate exists,
+// is finite and lies strictly between `lo` and `hi`.
+struct AssistBuildArgs {
+    uint32_t *bits;
+    const void *vol;
+    uint32_t f16, n, dilate;
+    float lo, hi;
+};
+__global__ void __launch_bounds__(256) assist_build_kernel(const __grid_constant__ AssistBuildArgs a);
 
 // Place one rank's compact (work-order) buffer into the full image.
 struct ScatterArgs {

@@ -32,6 +32,7 @@ int march_blocks_per_sm_host(int P);
 
 cudaError_t launch_shade(int mode, const ShadeArgs &a, unsigned grid, cudaStream_t s);
 cudaError_t launch_scatter(const ScatterArgs &a, unsigned grid, cudaStream_t s);
+cudaError_t launch_assist_build(const AssistBuildArgs &a, unsigned grid, cudaStream_t s);
 cudaError_t launch_ray_probe(int mode, float *out, const uint32_t *pixels, uint64_t n, const lyap_cam &cam, const lyap_params &prm, cudaStream_t s);
 cudaError_t launch_normalize(int mode, float *xyz, uint64_t n, cudaStream_t s);
 cudaError_t probe_peaks(double *ffma_ops, double *mufu_ops, double *clock_hz, int *sms);

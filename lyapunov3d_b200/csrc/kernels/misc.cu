@@ -33,6 +33,41 @@ __global__ void __launch_bounds__(256) scatter_kernel(const __grid_constant__ Sc
     }
 }
 
+__global__ void __launch_bounds__(256) assist_build_kernel(const __grid_constant__ AssistBuildArgs a)
+{
+    const uint64_t total = (uint64_t)a.n * a.n * a.n;
+    const uint64_t words = (total + 31) / 32;
+    const uint64_t stride = (uint64_t)gridDim.x * (blockDim.x / 32);
+    const unsigned lane = threadIdx.x & 31;
+    const int n = (int)a.n, d = (int)a.dilate;
+    for (uint64_t w = (uint64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32; w < words; w += stride) {
+        const uint64_t cell = w * 32 + lane;
+        bool safe = cell < total;
+        if (safe) {
+            const int ix = (int)(cell % a.n), iy = (int)((cell / a.n) % a.n), iz = (int)(cell / ((uint64_t)a.n * a.n));
+            if (ix - d < 0 || iy - d < 0 || iz - d < 0 || ix + 1 + d >= n || iy + 1 + d >= n || iz + 1 + d >= n) {
+                safe = false;
+            } else {
+                for (int z = iz - d; z <= iz + 1 + d && safe; ++z)
+                    for (int y = iy - d; y <= iy + 1 + d && safe; ++y)
+                        for (int x = ix - d; x <= ix + 1 + d; ++x) {
+                            const uint64_t k = (uint64_t)x + (uint64_t)a.n * ((uint64_t)y + (uint64_t)a.n * (uint64_t)z);
+                            const float v = a.f16 ? __half2float(reinterpret_cast<const __half *>(a.vol)[k]) : reinterpret_cast<const float *>(a.vol)[k];
+                            if (!(v > a.lo && v < a.hi)) { safe = false; break; }      // NaN fails both compares
+                        }
+            }
+        }
+        const unsigned word = __ballot_sync(0xffffffffu, safe);
+        if (lane == 0) a.bits[w] = word;
+    }
+}
+
+cudaError_t launch_assist_build(const AssistBuildArgs &a, unsigned grid, cudaStream_t s)
+{
+    assist_build_kernel<<<grid, 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_scatter(const ScatterArgs &a, unsigned grid, cudaStream_t s)
 {
     scatter_kernel<<<grid, 256, 0, s>>>(a);

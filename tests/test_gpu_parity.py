@@ -488,6 +488,52 @@ def test_hybrid_mode_tiles_and_guard_knobs(scene):
     assert frac_within(r3.cpu().numpy(), full_rgba.cpu().numpy(), PIXEL_TOL) >= PIXEL_FRAC
 
 
+def test_volume_assisted_march(scene):
+    """a baked volume lets the march step over samples in safely transparent cells.
+    (1) With no safe cell the call is the hybrid render, bit for bit.  (2) With the default conservative
+    classification it skips most of the march and still reproduces the non-assisted frame: hit point,
+    normal, exponent and pixel identical on >= 99.5 % of the pixels (north_star's image gate), evaluations
+    + skipped samples == the non-assisted evaluation count wherever the rays agree.  (3) Tile shards of an
+    assisted frame compose to the single-launch frame.  (4) With jitter on, the call is the parity mode."""
+    prm, cam, lights, n, seq = scene
+    p = clone(prm)
+    p.jitter = 0.0
+    w, h = 160, 96
+    c = clone(cam)
+    lp.scene_cam_recalculate(c, w, h, 1)
+    want_rgba, want_pts, want_ev = lp.render(c, p, seq, lights, n, w, h, mode="hybrid")
+    vol = lp.bake(p, seq, 128, mode="fast", dtype="f16")
+    none_safe = api.assist_build(vol, p, margin=100.0)
+    assert int(none_safe.count_nonzero()) == 0
+    r0, p0, e0, s0 = api.render_assisted(c, p, seq, lights, n, w, h, vol, none_safe)
+    assert torch.equal(r0, want_rgba) and torch.equal(p0, want_pts) and int(e0.item()) == int(want_ev.item()) and int(s0.item()) == 0
+
+    bits = api.assist_build(vol, p, margin=0.25, upper=0.0, dilate=1)
+    assert int(bits.count_nonzero()) > 0
+    r1, p1, e1, s1 = api.render_assisted(c, p, seq, lights, n, w, h, vol, bits)
+    a, b = points_np(p1), points_np(want_pts)
+    same = np.ones(a.shape, bool)
+    for f in ("P", "N", "l"):
+        eq = (a[f].view(np.uint32) == b[f].view(np.uint32)) | (np.isnan(a[f]) & np.isnan(b[f]))
+        same &= eq.reshape(a.shape + (-1,)).all(-1)
+    assert same.mean() >= PIXEL_FRAC, float(same.mean())
+    assert frac_within(r1.cpu().numpy(), want_rgba.cpu().numpy(), PIXEL_TOL) >= PIXEL_FRAC
+    assert int(s1.item()) > 0.2 * int(want_ev.item()), (int(s1.item()), int(want_ev.item()))        # a real saving
+    if same.all():
+        assert int(e1.item()) + int(s1.item()) == int(want_ev.item())
+
+    rgba, pts = torch.zeros_like(r1), torch.zeros_like(p1)
+    for r in range(3):
+        api.render_assisted(c, p, seq, lights, n, w, h, vol, bits, tile=8, rank=r, world=3, rgba=rgba, points=pts)
+    assert torch.equal(rgba, r1) and torch.equal(pts, p1)
+
+    cj = lp.render(c, prm, seq, lights, n, w, h, mode="exact")
+    rj = api.render_assisted(c, prm, seq, lights, n, w, h, vol, bits)
+    assert torch.equal(rj[0], cj[0]) and torch.equal(rj[1], cj[1]) and int(rj[3].item()) == 0
+    with pytest.raises(lp.LyapError):
+        api.render_assisted(c, p, seq, lights, n, w, h, vol, bits, mode="exact")
+
+
 def test_device_resident_sequence_is_accepted(scene):
     """The reference passes cudaSeq, a DEVICE copy of the sequence (lyap_interactive.cu:711,
     lyap_calculate.cu:72): the entry points take that pointer as well as the host array."""
@@ -750,7 +796,7 @@ def test_lyap_render_from_scene_file_reproduces_golden_twolights_frame(tmp_path,
     p0.jitter = 0.0
     l0 = clone(lights)
     l0[1].chaosColor.r = l0[1].chaosColor.g = l0[1].chaosColor.b = l0[1].chaosColor.a = 0.0
-    want = lp.render(cam, p0, lp.scene_convert_sequence(seq_s), l0, 2, 32, 32, mode="host")[0].cpu().numpy()
+    want = lp.render(cam, p0, lp.scene_convert_sequence(seq_s), l0, 2, 32, 32, mode="hybrid_host")[0].cpu().numpy()
     ppm = [f for f in os.listdir(tmp_path / "b") if f.endswith(".ppm")][0]
     vals = np.array(open(tmp_path / "b" / ppm).read().split()[4:], dtype=np.int64).reshape(32, 32, 3)
     assert np.array_equal(vals, want[..., :3])
@@ -823,3 +869,33 @@ def test_patched_reference_lyap_calculate_writes_identical_volume(tmp_path, scen
     vol = np.fromfile(tmp_path / "exps.raw", np.float32).reshape(512, 512, 512)
     prm, _, _, _, seq = scene
     assert same_floats(vol, lp.bake(prm, seq, 512, mode="exact").cpu().numpy())
+
+
+def test_reference_lyap_interactive_program_unmodified_vs_patched(tmp_path):
+    """The reference's own frame program, lyap_interactive.cu, run headless (integration/headless_gl_stubs:
+    no window, glutMainLoop runs display() once): init_scene -> update_scene -> render -> save_ppm / save_points
+    at its compiled-in 3840x2160.  Once UNMODIFIED with the unmodified kernel.cu, once with the one-line launch
+    swap of integration/lyap_interactive.patch against this library (EXACT mode; the reference build's aliased
+    normals switched on through LYAP_OPTIONS).  Both files it writes must be identical, byte for byte."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref_exe = os.path.join(root, "oracle", "_ref", "lyap_interactive_ref")
+    our_exe = os.path.join(root, "oracle", "_ref", "lyap_interactive_b200")
+    if not (os.path.exists(ref_exe) and os.path.exists(our_exe)):
+        pytest.skip("oracle/_ref/lyap_interactive_{ref,b200} not built")
+    need_gpu()
+    outs = {}
+    for tag, exe, env in (("ref", ref_exe, {}), ("b200", our_exe, {"LYAP_OPTIONS": "emulate_ref_nvcc_normals=1"})):
+        d = tmp_path / tag
+        os.makedirs(d)
+        r = subprocess.run([exe], cwd=d, capture_output=True, text=True, timeout=900, env=dict(os.environ, **env))
+        assert r.returncode == 0, (tag, r.stdout[-1000:], r.stderr[-1000:])
+        files = sorted(os.listdir(d))
+        ppm = [f for f in files if f.startswith("Render_") and f.endswith(".ppm")]
+        raw = [f for f in files if f.startswith("Points_") and f.endswith(".raw")]
+        assert len(ppm) == 1 and len(raw) == 1, files
+        assert "_3840x2160_BCABA_cx=" in ppm[0] and "_step=2_D=2.1_i=18,1008_d=4096_j=0.5_r=32_ot=-0.75_time=" in ppm[0]
+        outs[tag] = (open(d / ppm[0], "rb").read(), np.fromfile(d / raw[0], POINT_DTYPE))
+    assert len(outs["ref"][0]) > 3840 * 2160 * 12 and outs["ref"][0] == outs["b200"][0]              # the P3 PPM text
+    assert point_rows_equal(outs["b200"][1], outs["ref"][1]).all()                                  # every LyapPoint record

@@ -59,3 +59,53 @@ def test_logf_restatement_equals_this_machines_libm():
     assert (got.view(np.uint32) == want.view(np.uint32)).all()
     assert logf_model(np.array([1.0], np.float32), tab, poly)[0] == 0.0      # exact zero at x == 1, as glibc returns
     assert tab[9, 0] == 1.0 and tab[9, 1] == 0.0
+
+
+def test_merged_table_hot_loop_form_equals_libm_and_flags_everything_else():
+    """The hot-loop form of hostlog.cuh: one table indexed by (k mod 64, i) holding invc*2^-k and
+    logc + k*ln2, x used unreduced, and r^2 >= 2^-4 as the out-of-range test.  Restated in numpy
+    float64: inside the table's range it must give libm's logf bit for bit and never raise the flag;
+    outside (zero, subnormal, inf, nan, tiny, huge) it must always raise it."""
+    tab, poly = parse_header()
+    a0, a1, a2, ln2 = poly
+    text = open(os.path.join(ROOT, "lyapunov3d_b200", "csrc", "kernels", "hostlog.cuh")).read()
+    kmin = int(re.search(r"kLogfKmin\s*=\s*(-?\d+)", text).group(1))
+    e = np.arange(1024)
+    i, k = e & 15, (((e >> 4) + (-kmin)) & 63) + kmin
+    assert k.min() == kmin and k.max() == kmin + 63
+    invc_s = tab[i, 0] * np.ldexp(1.0, -k)                 # exact: a power-of-two scale
+    y0 = k.astype(np.float64) * ln2 + tab[i, 1]
+
+    def hot(x):
+        bits = x.view(np.uint32).astype(np.int64)
+        tmp = (bits - 0x3F330000) & 0xFFFFFFFF
+        idx = ((tmp >> 15) & 0x3FF0) >> 4
+        xd = np.abs(x).astype(np.float64)
+        with np.errstate(all="ignore"):
+            r = xd * invc_s[idx] - 1.0
+            r2 = r * r
+            odd = ~(r2 < 2.0 ** -4)                        # NaN counts as odd, as the unsigned compare of the high word does
+            y = a1 * r + a2
+            y = a0 * r2 + y
+            y = y * r2 + (y0[idx] + r)
+        return y.astype(np.float32), odd
+
+    libm = ctypes.CDLL(ctypes.util.find_library("m"))
+    libm.logf.restype = ctypes.c_float
+    libm.logf.argtypes = [ctypes.c_float]
+    rng = np.random.default_rng(12)
+    lo, hi = np.float32(2.0 ** (kmin + 1)).view(np.uint32), np.float32(11.0).view(np.uint32)
+    bits = np.concatenate([rng.integers(lo, hi, 60000), rng.integers(0x30000000, 0x40800000, 140000)]).astype(np.uint32)
+    x = bits.view(np.float32).copy()
+    x[::2] *= -1                                            # the hot loop sees r(1-2v) with its sign
+    got, odd = hot(x)
+    want = np.array([libm.logf(abs(float(v))) for v in x], np.float32)
+    assert not odd.any()
+    assert (got.view(np.uint32) == want.view(np.uint32)).all()
+    # every input outside the range must be flagged (the careful form then redoes the sample)
+    bad = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-45, 1e-39, -1e-40, 2.0 ** (kmin - 2), 2.0 ** (kmin - 40), 2.0 ** -126, 16.0, 100.0,
+                    3e38, -12.0, 2.0 ** 60, 2.0 ** 67], np.float32)
+    assert hot(bad)[1].all()
+    # in-range boundaries are not flagged
+    edge = np.array([2.0 ** (kmin + 1), 10.9, 1.0, 0.7, 1.4, 4.0, 2.0 ** -24], np.float32)
+    assert not hot(edge)[1].any()
