@@ -31,10 +31,10 @@ std::atomic<long> g_render_warps_per_sm{0};   // 0 = default
 std::atomic<long> g_bake_blocks_per_sm{0};    // 0 = occupancy maximum
 std::atomic<long> g_fast_redo{1};             // debug knob: 0 disables the safe re-evaluation in fast mode
 std::atomic<long> g_nvcc_normal_quirk{0};     // test knob: emulate the reference CUDA build's aliased normals
+std::atomic<long> g_tail_compaction{1};       // render_kernel's tail protocol (0 = off, for measurements)
 std::atomic<long> g_guard_batch{0};           // hybrid mode: parked lanes per warp that trigger a parity pass (0 = default)
 std::atomic<long> g_guard_scale{100};         // hybrid mode: guard band width in percent of the derived bound (test knob)
 
-constexpr int kDefaultRenderWarpsPerSM = 16;
 
 // ---------------------------------------------------------------- sequence plan
 const int kPeriods[] = {
@@ -228,6 +228,7 @@ int lyap_set_option(const char *key, long value)
     else if (!strcmp(key, "bake_blocks_per_sm")) g_bake_blocks_per_sm = value;
     else if (!strcmp(key, "emulate_ref_nvcc_normals")) g_nvcc_normal_quirk = value;
     else if (!strcmp(key, "fast_redo")) g_fast_redo = value;
+    else if (!strcmp(key, "tail_compaction")) g_tail_compaction = value;
     else if (!strcmp(key, "hybrid_guard_batch")) g_guard_batch = value;
     else if (!strcmp(key, "hybrid_guard_percent")) g_guard_scale = value;
     else return LYAP_ERR_BAD_ARGUMENT;
@@ -334,6 +335,8 @@ int render_impl(lyap_rgba *d_rgba, lyap_point *d_points, const lyap_cam *cam, co
     a.nvcc_normal_quirk = g_nvcc_normal_quirk.load() ? 1u : 0u;
     a.n_items = lyap_tile_count(width, height, tile, rank, world);
     a.evals = d_evals;
+    a.sm_count = (uint32_t)sc->sm_count;
+    a.tail_compaction = g_tail_compaction.load() ? 1u : 0u;
     if (a.n_items == 0) return LYAP_OK;
 
     cudaStream_t s = (cudaStream_t)stream;
@@ -402,17 +405,16 @@ int render_impl(lyap_rgba *d_rgba, lyap_point *d_points, const lyap_cam *cam, co
     int per_sm = by_mode(mode, [&] { return render_blocks_per_sm_exact(P); }, [&] { return render_blocks_per_sm_fast(P); },
                          [&] { return render_blocks_per_sm_host(P); });
     if (per_sm <= 0) return (int)cudaErrorLaunchOutOfResources;
-    long want_warps = g_render_warps_per_sm.load();
-    if (want_warps <= 0) {
-        // Each lane works through its rays one after the other and a ray cannot be split, so a
-        // launch ends with lanes idling while the longest rays finish.  With few rays per lane
-        // (small frames, or 1/8 of a frame per GPU) fewer persistent warps waste less in that tail
-        // than they lose in latency hiding (measured on 1/8 and 1/4 of a 1080p frame: -6 %/-10 %).
-        const unsigned long long items_per_sm = a.n_items / (unsigned long long)sc->sm_count;
-        want_warps = items_per_sm >= 6000 ? kDefaultRenderWarpsPerSM : (items_per_sm >= 2500 && mode != LYAP_MODE_FAST ? 12 : 8);
+    // Persistent warps: as many as the kernel's registers allow (4 blocks x 4 warps per SM for the exact
+    // evaluator, up to 6 x 4 for the host one).  A shard too small to give every lane a handful of rays
+    // used to want fewer warps (round 1: hand-tuned thresholds), because its launch ended with all
+    // resident warps dragging a few rays each; render_kernel now repacks those rays into fewer warps
+    // (tail compaction), so full occupancy is right at every shard size.  The knob stays for measurements.
+    const long want_warps = g_render_warps_per_sm.load();
+    if (want_warps > 0) {
+        const int want_blocks = (int)((want_warps * 32 + kRenderThreads - 1) / kRenderThreads);
+        if (want_blocks < per_sm) per_sm = want_blocks;
     }
-    int want_blocks = (int)((want_warps * 32 + kRenderThreads - 1) / kRenderThreads);
-    if (want_blocks < per_sm) per_sm = want_blocks;
     unsigned long long grid = (unsigned long long)sc->sm_count * per_sm;
     const unsigned long long max_useful = (a.n_items + kRenderThreads - 1) / kRenderThreads;
     if (grid > max_useful) grid = max_useful;

@@ -130,10 +130,9 @@ struct Accum<kExact> {
 template <>
 struct Accum<kHost> {
     float l;
-    bool odd;       // a rare logf input (0, subnormal, inf, nan) was seen: redo the sample carefully
-    bool careful;
+    bool odd;       // a rare logf input (0, subnormal, inf, nan, out of table range) was seen: look at the sample again
     LogfCtx ctx;
-    __device__ __forceinline__ void init() { l = 0.0f; odd = false; careful = false; ctx.init(); }
+    __device__ __forceinline__ void init() { l = 0.0f; odd = false; ctx.init(); }
     __device__ __forceinline__ void step(float r, float &v)
     {
         logistic_step<kHost>(r, v);
@@ -211,6 +210,42 @@ struct Accum<kFast> {
 // Out-of-line, rarely taken: the guaranteed-safe evaluation of one sample (defined below).
 static __device__ __noinline__ float fast_redo(const SeqPlan &sp, float x, float y, float z, float d);
 
+// Out-of-line, rarely taken: a HOST-mode sample whose speculative logf saw an input outside its table.
+// Nearly always that input is an exact zero derivative (an orbit that steps on v = 0.5: the x/y/z = 0
+// faces of a bake, ~6e-5 of a frame's samples), and then the answer is known without any logarithm:
+// logf(0) = -inf makes the float sum non-finite for good, i.e. the reference returns NAN
+// (kernel.cu:147-149).  So the orbit is replayed first (three FP32 operations per step) to look for a
+// zero; only a sample without one (subnormal, huge or non-finite derivatives) is evaluated again with
+// the careful logf.
+static __device__ __noinline__ float host_redo(const SeqPlan &sp, float x, float y, float z, float d)
+{
+    auto sel = [&](uint32_t s) { return sel4(s, x, y, z, d); };
+    {
+        float v = 0.5f;
+        bool zero = false;
+        RunCursor cur{0, 0};
+        run_steps(sp, cur, sp.settle, sel, [&](float r) { logistic_step<kHost>(r, v); }, [] {});
+        if (v != 0.5f) {   // kernel.cu:138: an orbit resting on 0.5 after settling skips the accumulation (l = 0)
+            run_steps(sp, cur, sp.accum, sel,
+                      [&](float r) {
+                          logistic_step<kHost>(r, v);
+                          zero = zero || (__fmaf_rn(-(r + r), v, r) == 0.0f);
+                      },
+                      [] {});
+            if (zero) return quiet_nan();
+        } else {
+            return 0.0f;   // the caller reports 0 / accum for this orbit whatever is returned here
+        }
+    }
+    float v = 0.5f;
+    Accum<kHost> acc;
+    acc.init();
+    RunCursor cur{0, 0};
+    run_steps(sp, cur, sp.settle, sel, [&](float r) { logistic_step<kHost>(r, v); }, [] {});
+    run_steps(sp, cur, sp.accum, sel, [&](float r) { acc.step_careful(r, v); }, [] {});
+    return acc.finish(sp, x, y, z, d, v);
+}
+
 template <int P>
 struct PeriodUnroll {
     static constexpr int U = (P >= 11) ? 1 : (20 / (P > 0 ? P : 1));  // periods per loop body
@@ -278,15 +313,7 @@ __device__ __forceinline__ float exponent(const SeqPlan &sp, float x, float y, f
     if constexpr (MODE == kHost) {
         // a zero / subnormal / non-finite derivative went through the speculative logf somewhere:
         // redo this sample with the exact special-case handling (rare; generic loop, small code)
-        if (acc.odd) {
-            float vv = 0.5f;
-            RunCursor cur{0, 0};
-            auto sel = [&](uint32_t s) { return sel4(s, x, y, z, d); };
-            run_steps(sp, cur, sp.settle, sel, [&](float r) { logistic_step<kHost>(r, vv); }, [] {});
-            acc.l = 0.0f;
-            run_steps(sp, cur, sp.accum, sel, [&](float r) { acc.step_careful(r, vv); }, [] {});
-            l = acc.finish(sp, x, y, z, d, vv);
-        }
+        if (acc.odd) l = host_redo(sp, x, y, z, d);
     }
     // reference kernel.cu:138: an orbit sitting on v == 0.5 after settling skips the
     // accumulation and reports l = 0 / accum

@@ -70,10 +70,12 @@ static __device__ const double kLogfPoly[5] = {-0x1.00ea348b88334p-2, 0x1.5575b0
 
 struct LogfCtx {
     double a0, a1, a2;
+    uint32_t tab;   // shared-window address of s_logf_tab
     __device__ __forceinline__ void init()
     {
         const volatile double *p = kLogfPoly;
         a0 = p[0]; a1 = p[1]; a2 = p[2];
+        tab = (uint32_t)__cvta_generic_to_shared(s_logf_tab);
     }
 };
 
@@ -123,11 +125,17 @@ static __device__ __noinline__ float glibc_logf_careful(float x)
 // in `odd` whether x fell outside the table's range (0, subnormal, inf, nan, |x| < ~2^-60 or >= ~2^4);
 // the caller redoes the whole sample with glibc_logf_careful when the flag comes back set.
 // Per step: 1 LDS.128, 6 FP64 ops, 2 conversions, 4 integer ops.
+// Byte offset of x's entry in s_logf_tab (stage 1 of the pipelined accumulator in exponent.cuh).
+__device__ __forceinline__ uint32_t glibc_logf_index(float x)
+{
+    // the sign bit of x falls out of the index mask, so |x| need not be formed for the lookup
+    return ((__float_as_uint(x) - 0x3f330000u) >> 15) & 0x3ff0u;
+}
+
 __device__ __forceinline__ float glibc_logf_speculative(float x, const LogfCtx &c, bool &odd)
 {
     // the sign bit of x falls out of the index mask, so |x| need not be formed for the lookup
-    const uint32_t tmp = __float_as_uint(x) - 0x3f330000u;
-    const double2 e = *reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(s_logf_tab) + ((tmp >> 15) & 0x3ff0u));
+    const double2 e = *reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(s_logf_tab) + glibc_logf_index(x));
     const double xd = (double)fabsf(x);
     const double r = __fma_rn(xd, e.x, -1.0);
     const double r2 = __dmul_rn(r, r);

@@ -163,6 +163,8 @@ struct RenderArgs {
     uint32_t assist_n, assist_f16;
     float assist_scale;                // n / 4: sample coordinate -> cell index
     unsigned long long *skipped;       // optional: += skipped samples
+    uint32_t sm_count;                 // SMs of the device (tail compaction: a block's slot on its SM)
+    uint32_t tail_compaction;          // 0 switches the tail protocol of render_kernel off
 };
 
 constexpr int kRenderThreads = 128;
@@ -193,23 +195,58 @@ __device__ __forceinline__ void finish_pixel(const RenderArgs &a, const RayState
     reinterpret_cast<uint32_t *>(a.rgba)[st.out] = shade_pixel<A>(pt, a.cam, a.lights, a.n_lights);
 }
 
+// Tail compaction.  The unit of SFU / FMA work is a warp-instruction: a warp with one live ray costs its
+// scheduler as much per evaluation as a full one.  Once the queue is empty the live rays thin out over
+// all resident warps, and with four warps per scheduler every remaining ray advances at a quarter of
+// the speed it would have alone -- the launch then ends 20-26 ms after its longest ray starts instead
+// of ~7 ms (one 1 576-evaluation ray at full speed).  So from the moment the queue is drained the four
+// warps of a block meet at a barrier once per evaluation, count their live rays, and whenever the rays
+// fit into fewer warps they are repacked through shared memory into the first warps (rotated by the
+// block's slot on its SM so that the survivors of co-resident blocks land on different schedulers);
+// the emptied warps exit.  Rays are independent and their state is moved verbatim: results do not change.
+struct TailShared {
+    int drained;            // some warp of the block saw the end of the queue
+    int cnt[2][4];          // live rays per warp, double-buffered by iteration parity
+    RayState pool[96];      // repacking buffer: a repack happens only when the rays fit into <= 3 warps
+};
+
+__device__ __forceinline__ void block_barrier(int warps)
+{
+    asm volatile("bar.sync 1, %0;" ::"r"(warps * 32) : "memory");
+}
+
+// Blocks per SM the compiler is asked to make room for: the exact evaluator wants registers for its software
+// pipeline (lg2 results three steps away from their use); the host evaluator is a ~150-cycle dependent
+// chain per step that the compiler will not interleave across steps, so it wants warps instead.
 template <int MODE, int P>
-__global__ void __launch_bounds__(kRenderThreads, 4) render_kernel(const __grid_constant__ RenderArgs a)
+struct RenderOccupancy { static constexpr int kBlocks = (MODE == kHost) ? (P <= 8 ? 6 : (P <= 20 ? 5 : 4)) : 4; };
+
+template <int MODE, int P>
+__global__ void __launch_bounds__(kRenderThreads, RenderOccupancy<MODE, P>::kBlocks) render_kernel(const __grid_constant__ RenderArgs a)
 {
     using A = typename ArithOf<MODE>::type;
+    __shared__ TailShared ts;
+    if (threadIdx.x == 0) ts.drained = 0;
     if constexpr (MODE == kHost) hostlog_init();
+    else __syncthreads();
 
     const unsigned full = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31;
+    const unsigned warp = threadIdx.x >> 5;
+    // this warp's rank in the repacking order: rotated by the block's slot among the blocks of its SM
+    const unsigned rot = (warp - (a.sm_count ? blockIdx.x / a.sm_count : 0u)) & 3u;
     RayState st;
     st.phase = kNeedRay;
     st.sx = st.sy = st.sz = 3.0f;   // idle lanes evaluate a harmless dummy point (not 2.0: that orbit is superstable)
-    bool drained = false;
+    bool drained = false, announced = false, solo = false;
+    int team = kRenderThreads / 32;   // warps of the block still taking part in the tail protocol
+    unsigned it = 0;
     unsigned long long evals = 0;
     // hybrid mode's second launch: the rays are the ones the march kernel listed
     const unsigned long long n_items = a.worklist ? *a.work_count : a.n_items;
 
     for (;;) {
+        if (!drained && *reinterpret_cast<volatile int *>(&ts.drained)) drained = true;
         // ---- refill idle lanes from the queue
         for (;;) {
             const bool need = st.phase == kNeedRay;
@@ -234,8 +271,50 @@ __global__ void __launch_bounds__(kRenderThreads, 4) render_kernel(const __grid_
             }
             if (base + n_need >= n_items) drained = true;
         }
-        const bool active = st.phase != kNeedRay;
-        if (__ballot_sync(full, active) == 0) break;
+        bool active = st.phase != kNeedRay;
+        const unsigned live_mask = __ballot_sync(full, active);
+
+        if (solo || !a.tail_compaction) {
+            if (live_mask == 0 && drained) break;
+        } else if (drained) {
+            // ---- tail protocol: every warp of the team gets here once per evaluation
+            if (!announced) {
+                announced = true;
+                if (lane == 0) *reinterpret_cast<volatile int *>(&ts.drained) = 1;
+            }
+            const unsigned buf = it++ & 1u;
+            if (lane == 0) ts.cnt[buf][warp] = __popc(live_mask);
+            block_barrier(team);
+            int total = 0, off = 0, live_warps = 0;
+#pragma unroll
+            for (unsigned r = 0; r < 4; ++r) {          // in repacking order; ranks >= team have left
+                const int c = (int)r < team ? ts.cnt[buf][(r + warp - rot) & 3u] : 0;
+                total += c;
+                live_warps += c > 0;
+                if (r < rot) off += c;
+            }
+            if (total == 0) break;
+            const int want = (total + 31) / 32;
+            if (want < live_warps || live_warps < team) {
+                // repack the block's live rays into the first `want` warps of the order; the rest leave
+                if (active) ts.pool[off + __popc(live_mask & ((1u << lane) - 1u))] = st;
+                block_barrier(team);
+                if ((int)rot >= want) break;
+                const int idx = (int)rot * 32 + (int)lane;
+                if (idx < total) {
+                    st = ts.pool[idx];
+                    active = true;
+                } else {
+                    st.phase = kNeedRay;
+                    st.sx = st.sy = st.sz = 3.0f;
+                    active = false;
+                }
+                team = want;
+                // the pool is reused by a later repack only after the next count barrier, which every
+                // remaining warp passes after it has read its rays here
+                if (want == 1) solo = true;
+            }
+        }
 
         // ---- one exponent for every lane (idle lanes evaluate a dummy point)
         const float l = exponent<MODE, P>(a.plan, st.sx, st.sy, st.sz, a.prm.d);
