@@ -414,6 +414,14 @@ int render_impl(lyap_rgba *d_rgba, lyap_point *d_points, const lyap_cam *cam, co
     if (want_warps > 0) {
         const int want_blocks = (int)((want_warps * 32 + kRenderThreads - 1) / kRenderThreads);
         if (want_blocks < per_sm) per_sm = want_blocks;
+    } else if (mode != LYAP_MODE_FAST) {
+        // A lane works through its rays one after the other, so when the queue runs dry every lane still
+        // holds a partly done ray: a residue of about one mean ray per lane that can no longer be balanced.
+        // With fewer than ~9 rays per lane that residue is > 10 % of the launch, and trading one block per
+        // SM (a quarter of the latency hiding, -1 % throughput on a full frame) for a third more rays per
+        // lane pays (measured on 1/4 and 1/8 of a 1080p frame: 74.5 -> 72.6 ms, 43.4 -> 41.6 ms).
+        const unsigned long long lanes = (unsigned long long)sc->sm_count * per_sm * kRenderThreads;
+        if (per_sm > 3 && a.n_items < 9ull * lanes) per_sm -= 1;
     }
     unsigned long long grid = (unsigned long long)sc->sm_count * per_sm;
     const unsigned long long max_useful = (a.n_items + kRenderThreads - 1) / kRenderThreads;

@@ -215,14 +215,13 @@ __device__ __forceinline__ void block_barrier(int warps)
     asm volatile("bar.sync 1, %0;" ::"r"(warps * 32) : "memory");
 }
 
-// Blocks per SM the compiler is asked to make room for: the exact evaluator wants registers for its software
-// pipeline (lg2 results three steps away from their use); the host evaluator is a ~150-cycle dependent
-// chain per step that the compiler will not interleave across steps, so it wants warps instead.
+// Four blocks of four warps per SM.  The exact evaluator wants the registers for its software pipeline (lg2
+// results three steps away from their use).  The host evaluator was tried at 5 and 6 blocks (80-96 registers):
+// no gain (1 244 vs 1 223 ms per 1080p frame) -- its step is bound by dispatch (18 instructions, of which
+// the six FP64 ones hold the dispatch port for two cycles each), not by latency, once four warps share a
+// scheduler.
 template <int MODE, int P>
-struct RenderOccupancy { static constexpr int kBlocks = (MODE == kHost) ? (P <= 8 ? 6 : (P <= 20 ? 5 : 4)) : 4; };
-
-template <int MODE, int P>
-__global__ void __launch_bounds__(kRenderThreads, RenderOccupancy<MODE, P>::kBlocks) render_kernel(const __grid_constant__ RenderArgs a)
+__global__ void __launch_bounds__(kRenderThreads, 4) render_kernel(const __grid_constant__ RenderArgs a)
 {
     using A = typename ArithOf<MODE>::type;
     __shared__ TailShared ts;
