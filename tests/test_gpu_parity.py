@@ -596,6 +596,32 @@ def test_tile_partition_is_bit_identical(scene, mode):
     assert torch.equal(rgba2, full_rgba) and torch.equal(pts2, full_pts)
 
 
+@pytest.mark.parametrize("mode", ["exact", "host", "fast", "hybrid", "hybrid_host"])
+def test_tail_compaction_does_not_change_a_single_byte(scene, mode):
+    """Once the queue is empty the kernels repack their remaining rays into fewer warps (block barrier per
+    evaluation, ray state moved through shared memory).  Rays are independent, so frames, records and
+    evaluation counts must be identical with the protocol on and off -- on a frame small enough that
+    nearly the whole launch IS the tail, on a shard of it, and on a 1080p-sized one."""
+    prm, cam, lights, n, seq = scene
+    p = clone(prm)
+    if mode.startswith("hybrid"):
+        p.jitter = 0.0
+    for (w, h, kw) in ((64, 40, {}), (200, 120, dict(tile=8, rank=1, world=3)), (480, 270, {})):
+        if mode in ("host", "hybrid_host") and w > 200:
+            continue
+        c = clone(cam)
+        lp.scene_cam_recalculate(c, w, h, 1)
+        out = []
+        for tc in (1, 0):
+            api.set_option("tail_compaction", tc)
+            try:
+                out.append(lp.render(c, p, seq, lights, n, w, h, mode=mode, **kw))
+            finally:
+                api.set_option("tail_compaction", 1)
+        assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1]), (mode, w, h)
+        assert int(out[0][2].item()) == int(out[1][2].item()), (mode, w, h)
+
+
 def test_host_buffer_api_equals_device_api(scene):
     prm, cam, lights, n, seq = scene
     c = clone(cam)
