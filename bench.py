@@ -507,6 +507,13 @@ def main():
         bound, note = "fp32", "FFMA-issue bound: %.3f FP32 lane-ops per iteration" % fp32_per_iter
         if args.mode != "fast":
             note += " (march samples, ~97.7 % of the evaluations; refinement and normals run on the parity evaluator)"
+    elif args.mode in ("host", "hybrid_host"):
+        # bit-exact glibc logf per step: 2 conversions (F2F f32<->f64) on the XU pipe, the pipe MUFU shares
+        # (16 lanes/clk/SM, measured by the MUFU.LG2 probe), 6 FP64 ops, 1 LDS.128; the tightest pipe is XU
+        xu_per_iter = 2.0 * prm.accum / iters_per_eval
+        peak = peaks["mufu_lane_ops_per_s"] / xu_per_iter / 1e9
+        bound, note = "xu", ("XU-pipe bound: %.3f F2F conversions per iteration (glibc-exact logf in FP64); the issue model "
+                             "(17.2 instructions + 6 double-dispatch FP64 per step) caps it at ~0.69 of this" % xu_per_iter)
     else:
         mufu_per_iter = prm.accum / iters_per_eval
         peak = peaks["mufu_lane_ops_per_s"] / mufu_per_iter / 1e9
@@ -529,7 +536,8 @@ def main():
                 "hbm_gbs_sanity": out_bytes / (t["step_ms"] * 1e-3) / 1e9}
     clk = (t["clocks"] or {}).get("sm_mhz") or (t["clocks"] or {}).get("sm_max_mhz")
     if clk:
-        lanes = 128.0 / ((2.0 * prm.settle + 4.0 * prm.accum) / iters_per_eval) if bound == "fp32" else 16.0 / (prm.accum / iters_per_eval)
+        lanes = (128.0 / ((2.0 * prm.settle + 4.0 * prm.accum) / iters_per_eval) if bound == "fp32" else
+                 16.0 / ((2.0 if bound == "xu" else 1.0) * prm.accum / iters_per_eval))
         roofline["frac_of_theoretical"] = achieved / (peaks["sm_count"] * lanes * clk * 1e6 / 1e9)
 
     cpu = None

@@ -119,6 +119,11 @@ struct Accum<kExact> {
         l = ArithDev::fma(ArithDev::lg2(fabsf(d)), 0.693147182f, l);
     }
     __device__ __forceinline__ void renorm() {}
+    template <class Body>
+    __device__ __forceinline__ void run_group(float &v, Body body)
+    {
+        body([&](float r, float &vv) { step(r, vv); });
+    }
     // +-inf and NaN are absorbing under the adds above, so the reference's per-step
     // isfinite() early-out (kernel.cu:147) equals one test here.
     __device__ __forceinline__ float finish(const SeqPlan &sp, float, float, float, float, float)
@@ -130,14 +135,14 @@ struct Accum<kExact> {
 template <>
 struct Accum<kHost> {
     float l;
-    bool odd;       // a rare logf input (0, subnormal, inf, nan, out of table range) was seen: look at the sample again
+    bool dead;      // the sum went non-finite for good (a true log(0) = -inf, inf or nan): the sample is NAN whatever follows
     LogfCtx ctx;
-    __device__ __forceinline__ void init() { l = 0.0f; odd = false; ctx.init(); }
+    __device__ __forceinline__ void init() { l = 0.0f; dead = false; ctx.init(); }
     __device__ __forceinline__ void step(float r, float &v)
     {
         logistic_step<kHost>(r, v);
         const float d = __fmaf_rn(-(r + r), v, r);
-        l = __fadd_rn(l, glibc_logf_speculative(d, ctx, odd));
+        l = __fadd_rn(l, glibc_logf_speculative(d, ctx));
     }
     __device__ __forceinline__ void step_careful(float r, float &v)
     {
@@ -145,7 +150,35 @@ struct Accum<kHost> {
         const float d = __fmaf_rn(-(r + r), v, r);
         l = __fadd_rn(l, glibc_logf_careful(fabsf(d)));
     }
+    // generic (run-length) loop: the speculative logf with an immediate careful retry of a poisoned step
+    __device__ __forceinline__ void step_checked(float r, float &v)
+    {
+        logistic_step<kHost>(r, v);
+        const float d = __fmaf_rn(-(r + r), v, r);
+        float y = glibc_logf_speculative(d, ctx);
+        if (y != y) y = glibc_logf_careful(fabsf(d));
+        l = __fadd_rn(l, y);
+    }
     __device__ __forceinline__ void renorm() {}
+    // One unrolled group of steps (a few periods, ~20 steps).  The hot loop's logf answers NaN for an
+    // input its table does not cover (zero, |d| < ~5e-6, inf, nan: ~3e-6 of the steps of a chaotic orbit),
+    // which turns the float sum NaN: the sum is looked at once per group, and a group that spoiled it
+    // is replayed from the saved (v, l) with the careful logf -- a few hundred instructions for the
+    // lanes concerned, once per ~10^3 groups, instead of a test per step or a replay of the sample.
+    // A sum that is still not finite after the careful replay is final (the reference returns NAN for
+    // it, kernel.cu:147-149); such a lane is not looked at again.
+    template <class Body>
+    __device__ __forceinline__ void run_group(float &v, Body body)
+    {
+        const float v0 = v, l0 = l;
+        body([&](float r, float &vv) { step(r, vv); });
+        if (!dead && !is_finite(l)) {
+            v = v0;
+            l = l0;
+            body([&](float r, float &vv) { step_careful(r, vv); });
+            dead = !is_finite(l);
+        }
+    }
     __device__ __forceinline__ float finish(const SeqPlan &sp, float, float, float, float, float)
     {
         return is_finite(l) ? __fdiv_rn(l, __uint2float_rn(sp.accum)) : quiet_nan();
@@ -182,6 +215,11 @@ struct Accum<kFast> {
         prod = __fmul_rn(prod, fabsf(q));
     }
     int bias_bits;   // = (127 + kBias) << 23, from SeqPlan::fold_bias
+    template <class Body>
+    __device__ __forceinline__ void run_group(float &v, Body body)
+    {
+        body([&](float r, float &vv) { step(r, vv); });
+    }
     __device__ __forceinline__ void renorm()
     {
         int bits = __float_as_int(prod);
@@ -209,42 +247,6 @@ struct Accum<kFast> {
 // -------------------------------------------------------------------- driver
 // Out-of-line, rarely taken: the guaranteed-safe evaluation of one sample (defined below).
 static __device__ __noinline__ float fast_redo(const SeqPlan &sp, float x, float y, float z, float d);
-
-// Out-of-line, rarely taken: a HOST-mode sample whose speculative logf saw an input outside its table.
-// Nearly always that input is an exact zero derivative (an orbit that steps on v = 0.5: the x/y/z = 0
-// faces of a bake, ~6e-5 of a frame's samples), and then the answer is known without any logarithm:
-// logf(0) = -inf makes the float sum non-finite for good, i.e. the reference returns NAN
-// (kernel.cu:147-149).  So the orbit is replayed first (three FP32 operations per step) to look for a
-// zero; only a sample without one (subnormal, huge or non-finite derivatives) is evaluated again with
-// the careful logf.
-static __device__ __noinline__ float host_redo(const SeqPlan &sp, float x, float y, float z, float d)
-{
-    auto sel = [&](uint32_t s) { return sel4(s, x, y, z, d); };
-    {
-        float v = 0.5f;
-        bool zero = false;
-        RunCursor cur{0, 0};
-        run_steps(sp, cur, sp.settle, sel, [&](float r) { logistic_step<kHost>(r, v); }, [] {});
-        if (v != 0.5f) {   // kernel.cu:138: an orbit resting on 0.5 after settling skips the accumulation (l = 0)
-            run_steps(sp, cur, sp.accum, sel,
-                      [&](float r) {
-                          logistic_step<kHost>(r, v);
-                          zero = zero || (__fmaf_rn(-(r + r), v, r) == 0.0f);
-                      },
-                      [] {});
-            if (zero) return quiet_nan();
-        } else {
-            return 0.0f;   // the caller reports 0 / accum for this orbit whatever is returned here
-        }
-    }
-    float v = 0.5f;
-    Accum<kHost> acc;
-    acc.init();
-    RunCursor cur{0, 0};
-    run_steps(sp, cur, sp.settle, sel, [&](float r) { logistic_step<kHost>(r, v); }, [] {});
-    run_steps(sp, cur, sp.accum, sel, [&](float r) { acc.step_careful(r, v); }, [] {});
-    return acc.finish(sp, x, y, z, d, v);
-}
 
 template <int P>
 struct PeriodUnroll {
@@ -279,41 +281,43 @@ __device__ __forceinline__ float exponent(const SeqPlan &sp, float x, float y, f
         const uint32_t groups = sp.accum_periods / U;
 #pragma unroll 1
         for (uint32_t g = 0; g < groups; g++) {
+            acc.run_group(v, [&](auto step) {
 #pragma unroll
-            for (int s = 0; s < U * P; s++) {
-                acc.step(r[s % P], v);
-                if ((s + 1) % Accum<kFast>::kFoldEvery == 0 || s + 1 == U * P) acc.renorm();
-            }
+                for (int s = 0; s < U * P; s++) {
+                    step(r[s % P], v);
+                    if ((s + 1) % Accum<kFast>::kFoldEvery == 0 || s + 1 == U * P) acc.renorm();
+                }
+            });
         }
         if constexpr (U > 1) {
 #pragma unroll 1
             for (uint32_t i = groups * U; i < sp.accum_periods; i++) {
+                acc.run_group(v, [&](auto step) {
 #pragma unroll
-                for (int k = 0; k < P; k++) acc.step(r[k], v);
-                acc.renorm();
+                    for (int k = 0; k < P; k++) step(r[k], v);
+                    acc.renorm();
+                });
             }
         }
+        acc.run_group(v, [&](auto step) {
 #pragma unroll 1
-        for (uint32_t n = 0; n < sp.accum_tail; n++) {
-            acc.step(sel4(sp.rot[n], x, y, z, d), v);
-            if ((n & 7) == 7) acc.renorm();
-        }
+            for (uint32_t n = 0; n < sp.accum_tail; n++) {
+                step(sel4(sp.rot[n], x, y, z, d), v);
+                if ((n & 7) == 7) acc.renorm();
+            }
+        });
     } else {
         RunCursor cur{0, 0};
         auto sel = [&](uint32_t s) { return sel4(s, x, y, z, d); };
         run_steps(sp, cur, sp.settle, sel, [&](float r) { logistic_step<MODE>(r, v); }, [] {});
         v_settled = v;
-        run_steps(sp, cur, sp.accum, sel, [&](float r) { acc.step(r, v); }, [&] { acc.renorm(); });
+        if constexpr (MODE == kHost) run_steps(sp, cur, sp.accum, sel, [&](float r) { acc.step_checked(r, v); }, [] {});
+        else run_steps(sp, cur, sp.accum, sel, [&](float r) { acc.step(r, v); }, [&] { acc.renorm(); });
     }
 
     float l = acc.finish(sp, x, y, z, d, v);
     if constexpr (MODE == kFast && P > 0) {
         if (acc.emin == 0 && sp.redo) return fast_redo(sp, x, y, z, d);   // zero or underflow: ask the safe loop
-    }
-    if constexpr (MODE == kHost) {
-        // a zero / subnormal / non-finite derivative went through the speculative logf somewhere:
-        // redo this sample with the exact special-case handling (rare; generic loop, small code)
-        if (acc.odd) l = host_redo(sp, x, y, z, d);
     }
     // reference kernel.cu:138: an orbit sitting on v == 0.5 after settling skips the
     // accumulation and reports l = 0 / accum

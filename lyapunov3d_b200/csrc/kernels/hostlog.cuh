@@ -34,30 +34,45 @@ static __device__ const double kLogfTab[32] = {
     0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2,  0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2};
 
 // Hot-loop form.  glibc splits x = 2^k * z and looks (invc, logc) up by the top four mantissa bits of
-// z; here ONE shared-memory table, indexed by the ten bits (k mod 64, i) of the shifted bit pattern,
-// holds the pair already combined with k:
+// z; here ONE shared-memory table, indexed by (k, i), holds the pair already combined with k:
 //     invc' = invc[i] * 2^-k      (a power-of-two scale: exact)     so  z*invc - 1 == x*invc' - 1
 //     y0    = logc[i] + k*ln2     (the same fused double expression the scalar form evaluates)
 // which removes the reduction of x to z, the int->double conversion of k and two of the eight FP64
 // operations from every step: r = fma((double)x, invc', -1); y = (A0 r^2 + (A1 r + A2)) r^2 + (y0 + r)
-// -- bit for bit the value of the scalar form for every x with k in [kLogfKmin, kLogfKmin + 63]
-// (2^-60 <= x < 2^4, roughly).  Anything else -- zero, subnormals, infinities, NaN, huge or tiny
-// magnitudes -- indexes a wrong entry, is caught by one unsigned range compare, and the caller redoes
-// the whole sample with the careful form (glibc's special cases included).
+// -- bit for bit the value of the scalar form for every x the table covers.
 //
-// A per-block copy in shared memory: the index differs per lane, which shared memory serves at full
-// rate and the constant cache would serialise.
-constexpr int kLogfKmin = -60;
-static __shared__ double2 s_logf_tab[1024];
+// Layout.  The index differs per lane, and a 16-byte entry read by eight lanes of a quarter-warp costs
+// one shared-memory wavefront per lane that shares a bank group with another one: measured on B200
+// (tools/probe_hostlog.cu, profiles/r02_probe_hostlog.md) a plain [k][i] table takes 9.5 wavefronts per
+// LDS.128 instead of 4 and the kernel is bound by the shared-memory pipe (98 % busy, 38.6 SMSP-cycles per
+// step against 24.8 without conflicts).  So every entry is stored EIGHT times, replica (lane & 7) in bank
+// group (lane & 7): conflict-free whatever the lanes look up.  That costs 128 bytes per entry, so the
+// table covers only the k that occur in practice -- kLogfKnum values from kLogfKmin up, i.e.
+// 2^kLogfKmin * 0.7 <= |x| < 5.6 (|r (1 - 2v)| <= 4 on the cube) -- plus ONE poison entry (0, NaN) to
+// which every other input (zero, subnormal, tiny, huge, inf, nan) is clamped by an unsigned minimum:
+// its logarithm comes out NaN and turns the caller's float sum NaN; the caller looks at the sum once
+// per unrolled group of ~20 steps and replays a spoiled group with the careful form (glibc's special
+// cases included; Accum<kHost>::run_group in exponent.cuh).  On a chaotic orbit ~3e-6 of the steps do
+// that, i.e. one group in ~10^4.
+constexpr int kLogfKmin = -17;
+constexpr int kLogfKnum = 20;
+constexpr uint32_t kLogfEntries = (uint32_t)kLogfKnum * 16u;                       // + 1 poison entry
+constexpr uint32_t kLogfOffK = 0x3f330000u - (uint32_t)(-kLogfKmin) * 0x00800000u;  // glibc's OFF moved down to k = kLogfKmin
+constexpr uint32_t kLogfSmemBytes = (kLogfEntries + 1u) * 128u;                     // dynamic shared memory of every HOST-mode kernel
+extern __shared__ __align__(128) unsigned char lyap_dyn_smem[];
 
 __device__ __forceinline__ void hostlog_init()
 {
-    for (unsigned e = threadIdx.x; e < 1024; e += blockDim.x) {
-        const int i = (int)(e & 15u);
-        const int k = (int)(((e >> 4) + (unsigned)(-kLogfKmin)) & 63u) + kLogfKmin;   // the k in range with k mod 64 == e >> 4
-        const double scale = __hiloint2double((1023 - k) << 20, 0);                   // 2^-k
-        s_logf_tab[e] = make_double2(__dmul_rn(kLogfTab[2 * i], scale),
-                                     __fma_rn((double)k, 0x1.62e42fefa39efp-1, kLogfTab[2 * i + 1]));
+    double2 *tab = reinterpret_cast<double2 *>(lyap_dyn_smem);
+    for (unsigned j = threadIdx.x; j < (kLogfEntries + 1u) * 8u; j += blockDim.x) {
+        const unsigned e = j >> 3;                       // replica j & 7 of entry e
+        double2 v = make_double2(0.0, __longlong_as_double(0x7ff8000000000000ll));
+        if (e < kLogfEntries) {
+            const int i = (int)(e & 15u), k = (int)(e >> 4) + kLogfKmin;
+            const double scale = __hiloint2double((1023 - k) << 20, 0);                   // 2^-k
+            v = make_double2(__dmul_rn(kLogfTab[2 * i], scale), __fma_rn((double)k, 0x1.62e42fefa39efp-1, kLogfTab[2 * i + 1]));
+        }
+        tab[j] = v;
     }
     __syncthreads();
 }
@@ -70,12 +85,12 @@ static __device__ const double kLogfPoly[5] = {-0x1.00ea348b88334p-2, 0x1.5575b0
 
 struct LogfCtx {
     double a0, a1, a2;
-    uint32_t tab;   // shared-window address of s_logf_tab
+    uint32_t base;     // shared-window address of this lane's replica of entry 0
     __device__ __forceinline__ void init()
     {
         const volatile double *p = kLogfPoly;
         a0 = p[0]; a1 = p[1]; a2 = p[2];
-        tab = (uint32_t)__cvta_generic_to_shared(s_logf_tab);
+        base = (uint32_t)__cvta_generic_to_shared(lyap_dyn_smem) + (threadIdx.x & 7u) * 16u;
     }
 };
 
@@ -121,28 +136,33 @@ static __device__ __noinline__ float glibc_logf_careful(float x)
     return glibc_logf_bits(ix);
 }
 
-// Speculative form for the hot loop: evaluates the merged-table path on |x| whatever it is and records
-// in `odd` whether x fell outside the table's range (0, subnormal, inf, nan, |x| < ~2^-60 or >= ~2^4);
-// the caller redoes the whole sample with glibc_logf_careful when the flag comes back set.
-// Per step: 1 LDS.128, 6 FP64 ops, 2 conversions, 4 integer ops.
-// Byte offset of x's entry in s_logf_tab (stage 1 of the pipelined accumulator in exponent.cuh).
-__device__ __forceinline__ uint32_t glibc_logf_index(float x)
+// Speculative form for the hot loop: the merged-table path on |x| whatever x is.  An input outside the
+// table comes back as NaN (poison entry); the caller tests its float SUM once per group of steps and
+// replays the group with glibc_logf_careful when it is not finite.
+// Per step: 4 integer ops, 1 LDS.128 (conflict-free), 6 FP64 ops, 2 conversions.
+__device__ __forceinline__ uint32_t glibc_logf_entry_addr(float x, uint32_t base)
 {
-    // the sign bit of x falls out of the index mask, so |x| need not be formed for the lookup
-    return ((__float_as_uint(x) - 0x3f330000u) >> 15) & 0x3ff0u;
+    // (bits << 1) drops the sign; t = 2 (|x| bits - OffK) is below kLogfKnum << 24 exactly for the x the
+    // table covers (any other x wraps to a larger unsigned value) and t >> 20 is the entry index.
+    // LEA, SHF, VIMNMX, LEA.  (Inline PTX: written in C the compiler rewrites the shift pair into add,
+    // shift and an extra mask.)
+    uint32_t e;
+    asm("{ .reg .u32 t;\n\t"
+        "shl.b32 t, %1, 1;\n\t"
+        "sub.u32 t, t, %2;\n\t"
+        "shr.u32 %0, t, 20; }"
+        : "=r"(e)
+        : "r"(__float_as_uint(x)), "n"(2u * kLogfOffK));
+    return base + (min(e, kLogfEntries) << 7);
 }
 
-__device__ __forceinline__ float glibc_logf_speculative(float x, const LogfCtx &c, bool &odd)
+__device__ __forceinline__ float glibc_logf_speculative(float x, const LogfCtx &c)
 {
-    // the sign bit of x falls out of the index mask, so |x| need not be formed for the lookup
-    const double2 e = *reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(s_logf_tab) + glibc_logf_index(x));
+    double2 e;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(e.x), "=d"(e.y) : "r"(glibc_logf_entry_addr(x, c.base)));
     const double xd = (double)fabsf(x);
     const double r = __fma_rn(xd, e.x, -1.0);
     const double r2 = __dmul_rn(r, r);
-    // Range check for free: with the right table entry |r| < 2^-4.5; with k off by a multiple of 64
-    // (or x zero / subnormal / inf / nan) r is -1, huge or NaN.  r^2 is non-negative, so one unsigned
-    // compare of its high word against 2^-4 catches them all.
-    odd = odd || ((uint32_t)__double2hiint(r2) >= 0x3fb00000u);
     double y = __fma_rn(c.a1, r, c.a2);
     y = __fma_rn(c.a0, r2, y);
     y = __fma_rn(y, r2, __dadd_rn(e.y, r));

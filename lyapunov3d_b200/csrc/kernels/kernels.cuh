@@ -707,7 +707,6 @@ template <int MODE>
 __global__ void __launch_bounds__(256) shade_kernel(const __grid_constant__ ShadeArgs a)
 {
     using A = typename ArithOf<MODE>::type;
-    if constexpr (MODE == kHost) hostlog_init();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.count; i += stride)
         reinterpret_cast<uint32_t *>(a.rgba)[i] = shade_pixel<A>(a.points[i], a.cam, a.lights, a.n_lights);

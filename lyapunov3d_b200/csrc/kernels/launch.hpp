@@ -13,6 +13,15 @@
 
 namespace lyap {
 
+// HOST-mode kernels keep their replicated logf table (hostlog.cuh) in dynamic shared memory; with the
+// kernels' static shared memory that is more than the 48 KiB a launch gets without opting in.
+constexpr size_t dyn_smem_of(int mode) { return mode == kHost ? (size_t)kLogfSmemBytes : 0; }
+template <class K>
+inline void opt_in_dyn_smem(K kernel, size_t bytes)
+{
+    if (bytes) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
 #define LYAP_DECLARE_MODE(NAME)                                                                          \
     cudaError_t launch_bake_##NAME(int P, const BakeArgs &a, unsigned grid, cudaStream_t s);              \
     cudaError_t launch_points_##NAME(int P, const PointsArgs &a, unsigned grid, cudaStream_t s);          \

@@ -9,7 +9,7 @@ namespace lyap {
 cudaError_t LYAP_CAT(launch_bake_, LYAP_TU_NAME)(int P, const BakeArgs &a, unsigned grid, cudaStream_t s)
 {
     switch (P) {
-#define X(p) case p: bake_kernel<LYAP_TU_MODE, p><<<grid, 256, 0, s>>>(a); break;
+#define X(p) case p: opt_in_dyn_smem(bake_kernel<LYAP_TU_MODE, p>, dyn_smem_of(LYAP_TU_MODE)); bake_kernel<LYAP_TU_MODE, p><<<grid, 256, dyn_smem_of(LYAP_TU_MODE), s>>>(a); break;
         LYAP_PERIODS(X)
 #undef X
     default: return cudaErrorInvalidValue;
@@ -20,7 +20,7 @@ cudaError_t LYAP_CAT(launch_bake_, LYAP_TU_NAME)(int P, const BakeArgs &a, unsig
 cudaError_t LYAP_CAT(launch_points_, LYAP_TU_NAME)(int P, const PointsArgs &a, unsigned grid, cudaStream_t s)
 {
     switch (P) {
-#define X(p) case p: points_kernel<LYAP_TU_MODE, p><<<grid, 256, 0, s>>>(a); break;
+#define X(p) case p: opt_in_dyn_smem(points_kernel<LYAP_TU_MODE, p>, dyn_smem_of(LYAP_TU_MODE)); points_kernel<LYAP_TU_MODE, p><<<grid, 256, dyn_smem_of(LYAP_TU_MODE), s>>>(a); break;
         LYAP_PERIODS(X)
 #undef X
     default: return cudaErrorInvalidValue;
@@ -32,7 +32,7 @@ int LYAP_CAT(bake_blocks_per_sm_, LYAP_TU_NAME)(int P)
 {
     int n = 0;
     switch (P) {
-#define X(p) case p: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, bake_kernel<LYAP_TU_MODE, p>, 256, 0); break;
+#define X(p) case p: opt_in_dyn_smem(bake_kernel<LYAP_TU_MODE, p>, dyn_smem_of(LYAP_TU_MODE)); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, bake_kernel<LYAP_TU_MODE, p>, 256, dyn_smem_of(LYAP_TU_MODE)); break;
         LYAP_PERIODS(X)
 #undef X
     default: break;

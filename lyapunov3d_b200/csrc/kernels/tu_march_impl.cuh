@@ -9,7 +9,7 @@ namespace lyap {
 cudaError_t LYAP_CAT(launch_march_, LYAP_TU_NAME)(int P, const RenderArgs &a, unsigned grid, cudaStream_t s)
 {
     switch (P) {
-#define X(p) case p: march_fast2_kernel<LYAP_TU_MODE, p><<<grid, kRenderThreads, 0, s>>>(a); break;
+#define X(p) case p: opt_in_dyn_smem(march_fast2_kernel<LYAP_TU_MODE, p>, dyn_smem_of(LYAP_TU_MODE)); march_fast2_kernel<LYAP_TU_MODE, p><<<grid, kRenderThreads, dyn_smem_of(LYAP_TU_MODE), s>>>(a); break;
         LYAP_PERIODS(X)
 #undef X
     default: return cudaErrorInvalidValue;
@@ -21,7 +21,7 @@ int LYAP_CAT(march_blocks_per_sm_, LYAP_TU_NAME)(int P)
 {
     int n = 0;
     switch (P) {
-#define X(p) case p: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, march_fast2_kernel<LYAP_TU_MODE, p>, kRenderThreads, 0); break;
+#define X(p) case p: opt_in_dyn_smem(march_fast2_kernel<LYAP_TU_MODE, p>, dyn_smem_of(LYAP_TU_MODE)); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, march_fast2_kernel<LYAP_TU_MODE, p>, kRenderThreads, dyn_smem_of(LYAP_TU_MODE)); break;
         LYAP_PERIODS(X)
 #undef X
     default: break;

@@ -19,7 +19,7 @@ struct RenderKernelOf<kFast, P> {
 cudaError_t LYAP_CAT(launch_render_, LYAP_TU_NAME)(int P, const RenderArgs &a, unsigned grid, cudaStream_t s)
 {
     switch (P) {
-#define X(p) case p: LYAP_RENDER_KERNEL(p)<<<grid, kRenderThreads, 0, s>>>(a); break;
+#define X(p) case p: opt_in_dyn_smem(LYAP_RENDER_KERNEL(p), dyn_smem_of(LYAP_TU_MODE)); LYAP_RENDER_KERNEL(p)<<<grid, kRenderThreads, dyn_smem_of(LYAP_TU_MODE), s>>>(a); break;
         LYAP_PERIODS(X)
 #undef X
     default: return cudaErrorInvalidValue;
@@ -31,7 +31,7 @@ int LYAP_CAT(render_blocks_per_sm_, LYAP_TU_NAME)(int P)
 {
     int n = 0;
     switch (P) {
-#define X(p) case p: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, LYAP_RENDER_KERNEL(p), kRenderThreads, 0); break;
+#define X(p) case p: opt_in_dyn_smem(LYAP_RENDER_KERNEL(p), dyn_smem_of(LYAP_TU_MODE)); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, LYAP_RENDER_KERNEL(p), kRenderThreads, dyn_smem_of(LYAP_TU_MODE)); break;
         LYAP_PERIODS(X)
 #undef X
     default: break;
