@@ -34,6 +34,7 @@ std::atomic<long> g_nvcc_normal_quirk{0};     // test knob: emulate the referenc
 std::atomic<long> g_tail_compaction{1};       // render_kernel's tail protocol (0 = off, for measurements)
 std::atomic<long> g_guard_batch{0};           // hybrid mode: parked lanes per warp that trigger a parity pass (0 = default)
 std::atomic<long> g_guard_scale{100};         // hybrid mode: guard band width in percent of the derived bound (test knob)
+std::atomic<long> g_seq_table{1};             // generic periods: per-lane multiplier table in shared memory (0 = run-length loop)
 
 
 // ---------------------------------------------------------------- sequence plan
@@ -89,6 +90,8 @@ int build_plan(SeqPlan &sp, const int32_t *seq, uint32_t settle, uint32_t accum)
         ++sp.n_runs;
         i = j;
     }
+    // generic path: the launchers drop the table again where its strips do not fit (launch.hpp)
+    sp.table_stride = (P == 0 && g_seq_table.load()) ? (L | 1u) : 0u;
     sp.settle_head = settle % L;
     sp.settle_periods = settle / L;
     sp.accum_periods = accum / L;
@@ -190,19 +193,6 @@ bool hybrid_mode(int mode) { return mode == LYAP_MODE_HYBRID || mode == LYAP_MOD
 // The evaluator whose results a mode reproduces (what bake / points / shade run for the hybrids).
 int parity_mode(int mode) { return mode == LYAP_MODE_HYBRID ? LYAP_MODE_EXACT : (mode == LYAP_MODE_HYBRID_HOST ? LYAP_MODE_HOST : mode); }
 
-// Half-width of the hybrid mode's guard band around a threshold `thr`.  The parity evaluators sum
-// `accum` float logarithms; each add rounds at half an ulp of the running sum, whose magnitude stays
-// below M = 2*|thr|*accum for a final exponent near thr, so the parity exponent lies within
-// ulp(M)/2 of the exact sum (the fast evaluator's own error is three orders smaller).  Twice that:
-float guard_half_width(float thr, uint32_t accum)
-{
-    double M = 2.0 * (fabs((double)thr) + 1e-3) * (double)(accum ? accum : 1);
-    if (M < 1.0) M = 1.0;
-    int e = 0;
-    frexp(M, &e);                 // M = f * 2^e, f in [0.5, 1): ulp_float(M) = 2^(e - 24)
-    return (float)ldexp(1.0, e - 24);
-}
-
 } // namespace
 
 extern "C" {
@@ -224,6 +214,7 @@ const char *lyap_error_string(int code)
 int lyap_set_option(const char *key, long value)
 {
     if (!strcmp(key, "force_generic")) g_force_generic = value;
+    else if (!strcmp(key, "seq_table")) g_seq_table = value;
     else if (!strcmp(key, "render_warps_per_sm")) g_render_warps_per_sm = value;
     else if (!strcmp(key, "bake_blocks_per_sm")) g_bake_blocks_per_sm = value;
     else if (!strcmp(key, "emulate_ref_nvcc_normals")) g_nvcc_normal_quirk = value;
@@ -355,10 +346,7 @@ int render_impl(lyap_rgba *d_rgba, lyap_point *d_points, const lyap_cam *cam, co
     if (hybrid_mode(mode) && prm->jitter == 0.0f) {
         if (a.n_items > 0xffffffffull) return LYAP_ERR_BAD_ARGUMENT;
         const bool host = mode == LYAP_MODE_HYBRID_HOST;
-        const double scale = (double)g_guard_scale.load() / 100.0;
-        a.guard[0] = (float)(scale * guard_half_width(prm->opaqueThreshold, prm->accum));
-        a.guard[1] = (float)(scale * guard_half_width(prm->chaosThreshold, prm->accum));
-        a.guard[2] = (float)(scale * guard_half_width(prm->nearThreshold, prm->accum));
+        a.guard_scale = (float)((double)g_guard_scale.load() / 100.0);
         const long gb = g_guard_batch.load();
         a.guard_batch = gb > 0 ? (uint32_t)(gb > 32 ? 32 : gb) : 1u;
         if (assist) {
@@ -376,7 +364,7 @@ int render_impl(lyap_rgba *d_rgba, lyap_point *d_points, const lyap_cam *cam, co
             if ((e = cudaMemsetAsync(mem, 0, 16, s)) != cudaSuccess) break;
             a.work_count = reinterpret_cast<unsigned long long *>(mem);
             a.worklist = reinterpret_cast<uint32_t *>(mem + 16);
-            int per_sm = host ? march_blocks_per_sm_host(P) : march_blocks_per_sm_exact(P);
+            int per_sm = host ? march_blocks_per_sm_host(P, a.plan) : march_blocks_per_sm_exact(P, a.plan);
             if (per_sm <= 0) { e = cudaErrorLaunchOutOfResources; break; }
             long want_warps = g_render_warps_per_sm.load();
             if (want_warps > 0 && (want_warps * 32 + kRenderThreads - 1) / kRenderThreads < per_sm)
@@ -390,7 +378,7 @@ int render_impl(lyap_rgba *d_rgba, lyap_point *d_points, const lyap_cam *cam, co
             RenderArgs b = a;
             b.queue = sc->counters + (sc->next.fetch_add(1) % kCounterRing);
             if ((e = cudaMemsetAsync(b.queue, 0, sizeof(unsigned long long), s)) != cudaSuccess) break;
-            per_sm = host ? render_blocks_per_sm_host(P) : render_blocks_per_sm_exact(P);
+            per_sm = host ? render_blocks_per_sm_host(P, a.plan) : render_blocks_per_sm_exact(P, a.plan);
             if (per_sm <= 0) { e = cudaErrorLaunchOutOfResources; break; }
             grid = (unsigned long long)sc->sm_count * per_sm;
             const unsigned long long max2 = (a.n_items + kRenderThreads - 1) / kRenderThreads;
@@ -402,8 +390,8 @@ int render_impl(lyap_rgba *d_rgba, lyap_point *d_points, const lyap_cam *cam, co
     }
     mode = parity_mode(mode);
 
-    int per_sm = by_mode(mode, [&] { return render_blocks_per_sm_exact(P); }, [&] { return render_blocks_per_sm_fast(P); },
-                         [&] { return render_blocks_per_sm_host(P); });
+    int per_sm = by_mode(mode, [&] { return render_blocks_per_sm_exact(P, a.plan); }, [&] { return render_blocks_per_sm_fast(P, a.plan); },
+                         [&] { return render_blocks_per_sm_host(P, a.plan); });
     if (per_sm <= 0) return (int)cudaErrorLaunchOutOfResources;
     // Persistent warps: as many as the kernel's registers allow (4 blocks x 4 warps per SM for the exact
     // evaluator, up to 6 x 4 for the host one).  A shard too small to give every lane a handful of rays
@@ -545,8 +533,8 @@ int lyap_bake(void *d_exps, int dtype, const lyap_params *prm, const int32_t *se
     a.f16 = dtype == LYAP_F16;
     a.nx = nx; a.ny = ny; a.nz = nz; a.z0 = z0; a.z1 = z1;
 
-    int per_sm = by_mode(mode, [&] { return bake_blocks_per_sm_exact(P); }, [&] { return bake_blocks_per_sm_fast(P); },
-                         [&] { return bake_blocks_per_sm_host(P); });
+    int per_sm = by_mode(mode, [&] { return bake_blocks_per_sm_exact(P, a.plan); }, [&] { return bake_blocks_per_sm_fast(P, a.plan); },
+                         [&] { return bake_blocks_per_sm_host(P, a.plan); });
     if (per_sm <= 0) return (int)cudaErrorLaunchOutOfResources;
     const long cap = g_bake_blocks_per_sm.load();
     if (cap > 0 && cap < per_sm) per_sm = (int)cap;

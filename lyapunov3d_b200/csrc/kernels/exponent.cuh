@@ -47,6 +47,7 @@ struct SeqPlan {
                               // (bits & mantissa) | bias stays ONE three-input LOP3
     uint32_t redo;            // fast mode: re-evaluate samples whose fold saw a zero exponent field (default 1)
     uint32_t n_runs;          // run-length form of the period (generic path): number of (symbol, length) pairs
+    uint32_t table_stride;    // generic path: entries per lane of the shared-memory multiplier table (len | 1), 0 = run-length loop
     uint8_t rot[kMaxPeriodRegs];  // sym rotated left by settle_head: the order both period loops see
     uint8_t sym[kMaxSeq];         // the period as written (register-table path)
     uint8_t runs[2 * kMaxSeq];    // (symbol, length <= 255) pairs covering one period (generic path)
@@ -89,6 +90,48 @@ __device__ __forceinline__ void run_steps(const SeqPlan &sp, RunCursor &cur, uin
 __device__ __forceinline__ float sel4(uint32_t s, float x, float y, float z, float d)
 {
     return s == 0 ? x : (s == 1 ? y : (s == 2 ? z : d));
+}
+
+// ------------------------------------------------- generic path: per-lane multiplier table
+// A period longer than the 32 registers of the unrolled path: the multiplier of every position of the
+// (rotated) period is written once per evaluation into a per-lane strip of dynamic shared memory and
+// read back with one LDS per step -- immediate offsets inside an 8-step unrolled block, the strip
+// stride (len | 1 entries) odd so that the 32 lanes of a warp hit 32 different banks.  An SFU-bound
+// exact step has 8 issue slots for its 6 instructions, so the load rides for free; the packed fast step
+// (two rays per lane, 8-byte entries) has 8 FMA-pipe cycles for 5 issue slots.  Periods whose strips
+// do not fit (launch.hpp) fall back to the run-length loop below.
+__device__ __forceinline__ uint32_t seq_table_base(const SeqPlan &sp, uint32_t entry_bytes)
+{
+    return (uint32_t)__cvta_generic_to_shared(lyap_dyn_smem) + threadIdx.x * sp.table_stride * entry_bytes;
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ unsigned long long lds_b64(uint32_t addr)
+{
+    unsigned long long v;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_b64(uint32_t addr, unsigned long long v) { asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory"); }
+
+// `count` consecutive table entries starting at `addr`: step(address) per entry, fold() after every 8 and at the end.
+template <int ESZ, class Step, class Fold>
+__device__ __forceinline__ void table_span(uint32_t addr, uint32_t count, Step step, Fold fold)
+{
+#pragma unroll 1
+    for (uint32_t n = count >> 3; n; --n, addr += 8 * ESZ) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) step(addr + j * ESZ);
+        fold();
+    }
+#pragma unroll 1
+    for (uint32_t n = count & 7u; n; --n, addr += ESZ) step(addr);
+    fold();
 }
 
 // ---------------------------------------------------------------- trajectory
@@ -253,8 +296,11 @@ struct PeriodUnroll {
     static constexpr int U = (P >= 11) ? 1 : (20 / (P > 0 ? P : 1));  // periods per loop body
 };
 
+// `strip_entry`: bytes per entry of the calling kernel's per-lane strips in the generic path's multiplier
+// table (4, or 8 in the two-rays-per-lane march kernel, whose warps alternate between this evaluator and
+// the packed one independently of each other: every thread must stay inside its own strip).
 template <int MODE, int P>
-__device__ __forceinline__ float exponent(const SeqPlan &sp, float x, float y, float z, float d)
+__device__ __forceinline__ float exponent(const SeqPlan &sp, float x, float y, float z, float d, uint32_t strip_entry = 4)
 {
     float v = 0.5f;
     Accum<MODE> acc;
@@ -307,12 +353,36 @@ __device__ __forceinline__ float exponent(const SeqPlan &sp, float x, float y, f
             }
         });
     } else {
-        RunCursor cur{0, 0};
-        auto sel = [&](uint32_t s) { return sel4(s, x, y, z, d); };
-        run_steps(sp, cur, sp.settle, sel, [&](float r) { logistic_step<MODE>(r, v); }, [] {});
-        v_settled = v;
-        if constexpr (MODE == kHost) run_steps(sp, cur, sp.accum, sel, [&](float r) { acc.step_checked(r, v); }, [] {});
-        else run_steps(sp, cur, sp.accum, sel, [&](float r) { acc.step(r, v); }, [&] { acc.renorm(); });
+        bool tabled = false;
+        if constexpr (MODE != kHost) tabled = sp.table_stride != 0;   // HOST mode's dynamic shared memory holds its logf table
+        if (tabled) {
+            const uint32_t T = seq_table_base(sp, strip_entry);
+            {
+                uint32_t pos = sp.settle_head, a = T;   // table in rotated order: entry k = position settle_head + k
+                for (uint32_t k = 0; k < sp.len; ++k, a += 4) {
+                    sts_f32(a, sel4(sp.sym[pos], x, y, z, d));
+                    pos = (pos + 1 == sp.len) ? 0 : pos + 1;
+                }
+            }
+            for (uint32_t n = 0; n < sp.settle_head; n++) logistic_step<MODE>(sel4(sp.sym[n], x, y, z, d), v);
+#pragma unroll 1
+            for (uint32_t i = 0; i < sp.settle_periods; i++)
+                table_span<4>(T, sp.len, [&](uint32_t a) { logistic_step<MODE>(lds_f32(a), v); }, [] {});
+            v_settled = v;
+            // (a hand-pipelined variant of this loop -- next block's multipliers prefetched, previous block's
+            // logs taken while the trajectory runs -- was slower: 0.71 against 0.79 of the SFU roofline)
+#pragma unroll 1
+            for (uint32_t i = 0; i < sp.accum_periods; i++)
+                table_span<4>(T, sp.len, [&](uint32_t a) { acc.step(lds_f32(a), v); }, [&] { acc.renorm(); });
+            table_span<4>(T, sp.accum_tail, [&](uint32_t a) { acc.step(lds_f32(a), v); }, [&] { acc.renorm(); });
+        } else {
+            RunCursor cur{0, 0};
+            auto sel = [&](uint32_t s) { return sel4(s, x, y, z, d); };
+            run_steps(sp, cur, sp.settle, sel, [&](float r) { logistic_step<MODE>(r, v); }, [] {});
+            v_settled = v;
+            if constexpr (MODE == kHost) run_steps(sp, cur, sp.accum, sel, [&](float r) { acc.step_checked(r, v); }, [] {});
+            else run_steps(sp, cur, sp.accum, sel, [&](float r) { acc.step(r, v); }, [&] { acc.renorm(); });
+        }
     }
 
     float l = acc.finish(sp, x, y, z, d, v);
@@ -398,24 +468,48 @@ struct AccumFast2 {
     }
 };
 
+// `guard` (optional): half-width of the band around a threshold inside which a PARITY evaluator's value
+// of this sample may lie on the other side (hybrid modes).  The fast value is accurate to ~1e-7; the
+// parity evaluators add `accum` float logs one by one, each add rounding by at most half an ulp of the
+// partial sum S_i, so they are off by at most ulp(max |S_i|) / 2 in units of l.  S_i = A_i + B_i with
+// A_i = sum log|1 - 2v| (every term <= 0: monotone, so A_i lies in [A, 0] for the final A the fast
+// evaluator holds) and B_i = sum log r over the symbols seen so far (between -Bneg and Bpos): hence
+// max |S_i| <= max(|A| + Bneg, Bpos).  The caller adds the parity evaluator's per-term error.
 __device__ __forceinline__ float fast_finish(const SeqPlan &sp, int esum, int emin, float prod, float x, float y, float z,
-                                             float d, float v)
+                                             float d, float v, float *guard = nullptr)
 {
     const float mant = __int_as_float((__float_as_int(prod) & 0x007fffff) | 0x3f800000);
-    double l2 = (double)esum + (double)__log2f(mant);
-    if (sp.cnt[0]) l2 += (double)sp.cnt[0] * (double)__log2f(fabsf(x));
-    if (sp.cnt[1]) l2 += (double)sp.cnt[1] * (double)__log2f(fabsf(y));
-    if (sp.cnt[2]) l2 += (double)sp.cnt[2] * (double)__log2f(fabsf(z));
-    if (sp.cnt[3]) l2 += (double)sp.cnt[3] * (double)__log2f(fabsf(d));
+    const float lgm = __log2f(mant);
+    double l2 = (double)esum + (double)lgm;
+    float bpos = 0.0f, bneg = 0.0f;   // float is plenty for the guard: only the binade of the bound matters
+    const float r4[4] = {x, y, z, d};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (sp.cnt[k]) {
+            const float lg = __log2f(fabsf(r4[k]));
+            l2 += (double)sp.cnt[k] * (double)lg;
+            if (guard) {
+                const float t = __uint2float_rn(sp.cnt[k]) * lg;
+                bpos += fmaxf(t, 0.0f);
+                bneg += fmaxf(-t, 0.0f);
+            }
+        }
+    }
     const float l = (float)(l2 * (0.6931471805599453 / (double)sp.accum));
     const bool bad = (emin == 0) || !is_finite(v) || !is_finite(l);
+    if (guard) {
+        // |A| = -(esum + log2 mant) >= 0; 1.001: the float arithmetic above must not land just under a binade
+        const float smax = fmaxf(bneg - ((float)esum + lgm), bpos) * (0.693147182f * 1.001f);
+        // half an ulp of smax: its exponent field, scaled by 2^-24 (0 for smax == 0, inf/nan stay so)
+        *guard = bad ? __int_as_float(0x7f800000) : __int_as_float(__float_as_int(smax) & 0x7f800000) * 5.9604644775390625e-8f;
+    }
     return bad ? quiet_nan() : l;
 }
 
 // Exponents of two sample points A and B in one pass (fast mode only).
 template <int P>
 __device__ __forceinline__ void exponent_fast2(const SeqPlan &sp, float xa, float ya, float za, float xb, float yb, float zb,
-                                               float d, float &la, float &lb)
+                                               float d, float &la, float &lb, float *ga = nullptr, float *gb = nullptr)
 {
     const f32x2 two = pack2(2.0f, 2.0f), one = pack2(1.0f, 1.0f);
     f32x2 w = pack2(-0.5f, -0.5f);
@@ -462,6 +556,23 @@ __device__ __forceinline__ void exponent_fast2(const SeqPlan &sp, float xa, floa
             acc.step(rpair(sp.rot[n]), w, two, one);
             if ((n & 7) == 7) acc.renorm();
         }
+    } else if (sp.table_stride != 0) {
+        const uint32_t T = seq_table_base(sp, 8);
+        {
+            uint32_t pos = sp.settle_head, a = T;
+            for (uint32_t k = 0; k < sp.len; ++k, a += 8) {
+                sts_b64(a, rpair(sp.sym[pos]));
+                pos = (pos + 1 == sp.len) ? 0 : pos + 1;
+            }
+        }
+        for (uint32_t n = 0; n < sp.settle_head; n++) settle_step(rpair(sp.sym[n]));
+#pragma unroll 1
+        for (uint32_t i = 0; i < sp.settle_periods; i++) table_span<8>(T, sp.len, [&](uint32_t a) { settle_step(lds_b64(a)); }, [] {});
+        unpack2(w, vsa, vsb);
+#pragma unroll 1
+        for (uint32_t i = 0; i < sp.accum_periods; i++)
+            table_span<8>(T, sp.len, [&](uint32_t a) { acc.step(lds_b64(a), w, two, one); }, [&] { acc.renorm(); });
+        table_span<8>(T, sp.accum_tail, [&](uint32_t a) { acc.step(lds_b64(a), w, two, one); }, [&] { acc.renorm(); });
     } else {
         RunCursor cur{0, 0};
         run_steps(sp, cur, sp.settle, rpair, settle_step, [] {});
@@ -472,10 +583,11 @@ __device__ __forceinline__ void exponent_fast2(const SeqPlan &sp, float xa, floa
     float pa, pb, wa, wb;
     unpack2(acc.prod, pa, pb);
     unpack2(w, wa, wb);
-    la = fast_finish(sp, acc.esum0, acc.emin0, pa, xa, ya, za, d, wa);
-    lb = fast_finish(sp, acc.esum1, acc.emin1, pb, xb, yb, zb, d, wb);
+    la = fast_finish(sp, acc.esum0, acc.emin0, pa, xa, ya, za, d, wa, ga);
+    lb = fast_finish(sp, acc.esum1, acc.emin1, pb, xb, yb, zb, d, wb, gb);
     if constexpr (P > 0) {
         // zero derivative or (with the 20-step folds) a possible underflow: ask the safe loop
+        // (its guard stays infinite: a hybrid caller leaves such a sample to the parity evaluator)
         if (acc.emin0 == 0 && sp.redo) la = fast_redo(sp, xa, ya, za, d);
         if (acc.emin1 == 0 && sp.redo) lb = fast_redo(sp, xb, yb, zb, d);
     }

@@ -152,7 +152,7 @@ struct RenderArgs {
     // refine kernel (render_kernel with `worklist` set) takes its rays from the list.
     uint32_t *worklist;
     unsigned long long *work_count;
-    float guard[3];                    // half-width of the guard band around opaque / chaos / near threshold
+    float guard_scale;                 // test knob: factor on the per-sample guard band (1 = the derived bound, 0 = no band)
     uint32_t guard_batch;              // parked lanes per warp that trigger a parity-evaluator pass
     // volume-assisted march: a baked exponent volume classifies the cells of its grid;
     // march samples that fall into a cell whose whole neighbourhood is safely transparent are not
@@ -530,9 +530,9 @@ __global__ void __launch_bounds__(kRenderThreads, 3) render_fast2_kernel(const _
 // thresholds (kernel.cu:326,370-384), so the march -- 97.7 % of all evaluations -- can run on the
 // packed fast evaluator, two rays per lane, while refinement and normals (whose exponents end up
 // in the LyapPoint record and in the pixel) stay on the parity evaluator MODE (kExact or kHost).
-// A fast exponent that lies inside a guard band around a threshold (a.guard[], sized from the
-// rounding-error bound of the reference's float summation, abi.cu) could compare differently from
-// the parity evaluator's: that slot is parked and the warp re-evaluates its parked samples with
+// A fast exponent that lies inside a guard band around a threshold -- sized per sample from a bound on
+// the rounding error of the parity evaluator's float summation (fast_finish in exponent.cuh) -- could
+// compare differently from the parity evaluator's: that slot is parked and the warp re-evaluates its parked samples with
 // exponent<MODE> once `guard_batch` lanes hold one (or nothing else is left to do).  Hit point,
 // normal, exponent and pixel are therefore those of the parity mode; only the cloud sums a and c
 // (sums of the march exponents themselves) carry the fast evaluator's last-bit differences.
@@ -609,10 +609,14 @@ __global__ void __launch_bounds__(kRenderThreads, 3) march_fast2_kernel(const __
         }
         retire(s);
     };
-    auto in_guard = [&](float l) {
+    // g: the sample's own bound on the parity evaluator's summation error (fast_finish), plus that
+    // evaluator's error per term -- lg2.approx is good to 2^-22 (1 + |log2 d|), glibc's logf to an ulp
+    // of a term of magnitude <= 17
+    constexpr float kTermEps = (MODE == kHost) ? 2e-6f : 1e-6f;
+    auto in_guard = [&](float l, float g) {
+        const float w = (g + kTermEps) * a.guard_scale;
         // NaN lands here too: the parity evaluator decides
-        return !(fabsf(l - a.prm.opaqueThreshold) >= a.guard[0] && fabsf(l - a.prm.chaosThreshold) >= a.guard[1] &&
-                 fabsf(l - a.prm.nearThreshold) >= a.guard[2]);
+        return !(fabsf(l - a.prm.opaqueThreshold) >= w && fabsf(l - a.prm.chaosThreshold) >= w && fabsf(l - a.prm.nearThreshold) >= w);
     };
 
     for (;;) {
@@ -661,21 +665,21 @@ __global__ void __launch_bounds__(kRenderThreads, 3) march_fast2_kernel(const __
             // a parked slot sits the fast pass out on the dummy point: its own sample may well be a
             // zero-derivative one (NaN parks too), which would drag the warp through the fast
             // evaluator's out-of-line safe loop on every pass until the parity pass comes
-            float l[2];
+            float l[2], g[2];
             exponent_fast2<P>(a.plan, park0 ? 3.0f : st[0].Px, park0 ? 3.0f : st[0].Py, park0 ? 3.0f : st[0].Pz,
-                              park1 ? 3.0f : st[1].Px, park1 ? 3.0f : st[1].Py, park1 ? 3.0f : st[1].Pz, a.prm.d, l[0], l[1]);
+                              park1 ? 3.0f : st[1].Px, park1 ? 3.0f : st[1].Py, park1 ? 3.0f : st[1].Pz, a.prm.d, l[0], l[1], &g[0], &g[1]);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 if (j == 0 ? fast0 : fast1) {
                     ++evals;
-                    if (in_guard(l[j])) st[j].phase |= kGuardBit;
+                    if (in_guard(l[j], g[j])) st[j].phase |= kGuardBit;
                     else consume(st[j], l[j]);
                 }
             }
         } else {
             // one parked sample per lane through the parity evaluator (slot 0 first)
             const float x = park0 ? st[0].Px : st[1].Px, y = park0 ? st[0].Py : st[1].Py, z = park0 ? st[0].Pz : st[1].Pz;
-            const float l = exponent<MODE, P>(a.plan, x, y, z, a.prm.d);
+            const float l = exponent<MODE, P>(a.plan, x, y, z, a.prm.d, 8);
             if (park0) { st[0].phase &= ~kGuardBit; consume(st[0], l); }
             else if (park1) { st[1].phase &= ~kGuardBit; consume(st[1], l); }
         }

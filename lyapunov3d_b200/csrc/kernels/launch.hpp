@@ -13,9 +13,27 @@
 
 namespace lyap {
 
-// HOST-mode kernels keep their replicated logf table (hostlog.cuh) in dynamic shared memory; with the
-// kernels' static shared memory that is more than the 48 KiB a launch gets without opting in.
+// Dynamic shared memory of a launch.  HOST-mode kernels keep their replicated logf table (hostlog.cuh)
+// there; the generic-period path of the other modes keeps its per-lane multiplier table there
+// (exponent.cuh: plan.table_stride entries of `entry_bytes` per thread).  Either can exceed the 48 KiB a
+// launch gets without opting in.
+constexpr size_t kSeqTableMaxBytes = 56 * 1024;   // per block: four render blocks per SM stay resident
 constexpr size_t dyn_smem_of(int mode) { return mode == kHost ? (size_t)kLogfSmemBytes : 0; }
+inline size_t seq_table_bytes(int mode, const SeqPlan &plan, size_t entry_bytes, size_t threads)
+{
+    return mode == kHost ? 0 : (size_t)plan.table_stride * entry_bytes * threads;
+}
+// Generic-period launches take their table when it fits and the run-length loop otherwise.
+template <class Args>
+inline size_t settle_seq_table(int mode, Args &a, size_t entry_bytes, size_t threads)
+{
+    const size_t bytes = seq_table_bytes(mode, a.plan, entry_bytes, threads);
+    if (bytes > kSeqTableMaxBytes) {
+        a.plan.table_stride = 0;
+        return 0;
+    }
+    return bytes;
+}
 template <class K>
 inline void opt_in_dyn_smem(K kernel, size_t bytes)
 {
@@ -26,8 +44,9 @@ inline void opt_in_dyn_smem(K kernel, size_t bytes)
     cudaError_t launch_bake_##NAME(int P, const BakeArgs &a, unsigned grid, cudaStream_t s);              \
     cudaError_t launch_points_##NAME(int P, const PointsArgs &a, unsigned grid, cudaStream_t s);          \
     cudaError_t launch_render_##NAME(int P, const RenderArgs &a, unsigned grid, cudaStream_t s);          \
-    int render_blocks_per_sm_##NAME(int P);                                                               \
-    int bake_blocks_per_sm_##NAME(int P);
+    int render_blocks_per_sm_##NAME(int P, const SeqPlan &plan);                                          \
+    int bake_blocks_per_sm_##NAME(int P, const SeqPlan &plan);                                            \
+    int bake_threads_##NAME(const SeqPlan &plan);
 
 LYAP_DECLARE_MODE(exact)
 LYAP_DECLARE_MODE(fast)
@@ -36,8 +55,8 @@ LYAP_DECLARE_MODE(host)
 // hybrid mode's march kernel (packed fast evaluator + parity evaluator NAME for the guard bands)
 cudaError_t launch_march_exact(int P, const RenderArgs &a, unsigned grid, cudaStream_t s);
 cudaError_t launch_march_host(int P, const RenderArgs &a, unsigned grid, cudaStream_t s);
-int march_blocks_per_sm_exact(int P);
-int march_blocks_per_sm_host(int P);
+int march_blocks_per_sm_exact(int P, const SeqPlan &plan);
+int march_blocks_per_sm_host(int P, const SeqPlan &plan);
 
 cudaError_t launch_shade(int mode, const ShadeArgs &a, unsigned grid, cudaStream_t s);
 cudaError_t launch_scatter(const ScatterArgs &a, unsigned grid, cudaStream_t s);

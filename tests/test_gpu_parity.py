@@ -133,15 +133,75 @@ def test_generic_sequence_loop_equals_unrolled_periods(scene, mode):
     a = lp.bake(prm, seq, 24, 16, 8, mode=mode).cpu().numpy()
     api.set_option("force_generic", 1)
     try:
-        b = lp.bake(prm, seq, 24, 16, 8, mode=mode).cpu().numpy()
+        for table in (1, 0):             # shared-memory multiplier table, run-length loop
+            api.set_option("seq_table", table)
+            b = lp.bake(prm, seq, 24, 16, 8, mode=mode).cpu().numpy()
+            if mode == "fast":
+                assert close_nan(a, b, 2e-5), table     # the fold cadence differs, the value is the same
+            else:
+                assert same_floats(a, b), table
         long_seq = lp.scene_convert_sequence("A9B9C9D9")           # 40 symbols: always generic
         assert api.plan_period(long_seq, 18, 1008) == 0
     finally:
         api.set_option("force_generic", 0)
-    if mode == "fast":
-        assert close_nan(a, b, 2e-5)     # the fold cadence differs, the value is the same
-    else:
-        assert same_floats(a, b)
+        api.set_option("seq_table", 1)
+
+
+def test_long_period_table_path_equals_run_length_loop(scene):
+    """Periods above 32 symbols: the per-lane multiplier table in shared memory (default) against the
+    run-length loop (seq_table = 0) -- bake, points and frames, with settle counts that are not
+    multiples of the period, and periods whose table no longer fits (the launcher falls back)."""
+    prm0, cam, lights, n, _ = scene
+    c = clone(cam)
+    lp.scene_cam_recalculate(c, 48, 32, 1)
+    rng = np.random.default_rng(5)
+    seqs = ["A9B9C9D9", "A9A8B9B9", "ABCDABCDABCDABCDABCDABCDABCDABCDABCDA",
+            "".join("ABC"[i] for i in rng.integers(0, 3, 53)),        # 53: fits as 4-byte entries and as pairs
+            "".join("ABC"[i] for i in rng.integers(0, 3, 97)),        # 97: fits as 4-byte entries only
+            "".join("AB"[i] for i in rng.integers(0, 2, 301))]        # 301: never fits
+    xyz = torch.tensor(rng.uniform(0.5, 4.0, (4096, 3)), dtype=torch.float32, device="cuda")
+    try:
+        for s_txt in seqs:
+            seq = lp.scene_convert_sequence(s_txt)
+            for settle, accum in ((18, 1008), (7, 333)):
+                prm = clone(prm0)
+                prm.settle, prm.accum, prm.d = settle, accum, 3.2
+                assert api.plan_period(seq, settle, accum) == 0
+                got = {}
+                for table in (1, 0):
+                    api.set_option("seq_table", table)
+                    got[table] = dict(
+                        be=lp.bake(prm, seq, 20, 10, 6, mode="exact").cpu().numpy(),
+                        bf=lp.bake(prm, seq, 20, 10, 6, mode="fast").cpu().numpy(),
+                        pe=lp.exponent_points(xyz, prm, seq, mode="exact").cpu().numpy(),
+                        pf=lp.exponent_points(xyz, prm, seq, mode="fast").cpu().numpy())
+                    if accum == 333:
+                        pj = clone(prm)
+                        pj.jitter = 0.0
+                        got[table]["re"] = lp.render(c, prm, seq, lights, n, 48, 32, mode="exact")
+                        got[table]["rf"] = lp.render(c, prm, seq, lights, n, 48, 32, mode="fast")
+                        got[table]["rh"] = lp.render(c, pj, seq, lights, n, 48, 32, mode="hybrid")
+                        got[table]["rp"] = lp.render(c, pj, seq, lights, n, 48, 32, mode="exact")
+                t, r = got[1], got[0]
+                assert same_floats(t["be"], r["be"]) and same_floats(t["pe"], r["pe"]), (len(s_txt), settle)
+                assert close_nan(t["bf"], r["bf"], 2e-5) and close_nan(t["pf"], r["pf"], 2e-5), (len(s_txt), settle)
+                if accum == 333:
+                    assert torch.equal(t["re"][0], r["re"][0]) and torch.equal(t["re"][1], r["re"][1]), len(s_txt)
+                    assert int(t["re"][2].item()) == int(r["re"][2].item())
+                    # hybrid: hit point, normal and exponent are the parity evaluator's either way; the cloud sums
+                    # a/c are sums of fast march exponents (fold cadence differs), so a channel may round differently
+                    # (the per-sample guard band holds for any sequence and iteration count: both equal the parity mode)
+                    ta, ra, pa = points_np(t["rh"][1]), points_np(r["rh"][1]), points_np(t["rp"][1])
+                    for f in ("P", "N", "l"):
+                        assert same_floats(ta[f], pa[f]) and same_floats(ra[f], pa[f]), (len(s_txt), f)
+                    assert int(t["rh"][2].item()) == int(r["rh"][2].item()) == int(t["rp"][2].item())
+                    assert (t["rh"][0].int() - r["rh"][0].int()).abs().max().item() <= 1, len(s_txt)
+                    assert (t["rh"][0].int() - t["rp"][0].int()).abs().max().item() <= 1, len(s_txt)
+                    # fast frames: same evaluator up to the fold cadence; chaotic pixels may differ
+                    same = (t["rf"][0] == r["rf"][0]).all(dim=-1).float().mean().item()
+                    assert same > 0.9, (len(s_txt), same)
+    finally:
+        api.set_option("seq_table", 1)
 
 
 def test_long_sequence_against_oracle(oracle, scene):
