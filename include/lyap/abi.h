@@ -66,7 +66,9 @@ const char *lyap_error_string(int code);
 
 /* Tuning / test knobs: "render_warps_per_sm" (persistent warps per SM, default 16),
  * "bake_blocks_per_sm" (cap; 0 = occupancy maximum), "force_generic" (1 = always use
- * the per-step-select exponent loop instead of a period instantiation),
+ * the generic-period path instead of a period instantiation), "seq_table" (generic path:
+ * 0 = run-length loop, 2 = per-lane multiplier table in shared memory wherever it fits,
+ * 1 = default: the table for sequences whose runs average below 14 steps),
  * "emulate_ref_nvcc_normals" (test knob: reproduce the normals the reference's CUDA
  * build produces under nvcc 12.9, where ls[] aliases lyap4d's abcd[]),
  * "hybrid_guard_batch" (parked lanes per warp that trigger a parity pass; 0 = default = 1),
@@ -75,7 +77,7 @@ const char *lyap_error_string(int code);
  * several threads, not concurrently with launches. */
 int lyap_set_option(const char *key, long value);
 /* Which unrolled-period instantiation a sequence runs on: its period's smallest
- * compiled multiple, 0 for the generic loop, -1 for an invalid sequence. */
+ * compiled multiple (1..32, 36, 40), 0 for the generic path, -1 for an invalid sequence. */
 int lyap_plan_period(const int32_t *seq, uint32_t settle, uint32_t accum);
 /* Test hook: dumps the iteration schedule built for a sequence (see csrc/abi.cu). */
 int lyap_plan_describe(const int32_t *seq, uint32_t settle, uint32_t accum, uint32_t *header, uint8_t *sym, uint8_t *rot, uint8_t *runs);

@@ -205,12 +205,12 @@ def plan_describe(seq, settle, accum):
     """The iteration schedule (SeqPlan) the library builds for a sequence; for tests."""
     seq = np.ascontiguousarray(seq, np.int32)
     hdr = np.zeros(11, np.uint32)
-    sym, rot, runs = np.zeros(1024, np.uint8), np.zeros(32, np.uint8), np.zeros(2048, np.uint8)
+    sym, rot, runs = np.zeros(1024, np.uint8), np.zeros(64, np.uint8), np.zeros(2048, np.uint8)
     _check(lib().lyap_plan_describe(seq.ctypes.data, settle, accum, hdr.ctypes.data, sym.ctypes.data, rot.ctypes.data,
                                     runs.ctypes.data), "lyap_plan_describe")
     P, ln, sh, sp_, ap, at = (int(v) for v in hdr[:6])
     return {"P": P, "len": ln, "settle_head": sh, "settle_periods": sp_, "accum_periods": ap, "accum_tail": at,
-            "cnt": [int(v) for v in hdr[6:10]], "sym": sym[:ln].tolist(), "rot": rot[:min(ln, 32)].tolist(),
+            "cnt": [int(v) for v in hdr[6:10]], "sym": sym[:ln].tolist(), "rot": rot[:min(ln, 40)].tolist(),
             "runs": runs[:2 * int(hdr[10])].reshape(-1, 2).tolist()}
 
 

@@ -90,8 +90,14 @@ int build_plan(SeqPlan &sp, const int32_t *seq, uint32_t settle, uint32_t accum)
         ++sp.n_runs;
         i = j;
     }
-    // generic path: the launchers drop the table again where its strips do not fit (launch.hpp)
-    sp.table_stride = (P == 0 && g_seq_table.load()) ? (L | 1u) : 0u;
+    // Generic path: a per-lane multiplier table in shared memory costs one LDS per step, the run-length
+    // loop ~25 instructions per run.  Measured on B200 (profiles/r02_longseq.log): runs of ~20 (A9A8B9B9)
+    // 0.83 against 0.75 of the SFU roofline in favour of the run-length loop, runs of 10 (A9B9C9D9) 0.71
+    // against 0.79 in favour of the table, an irregular 53-symbol sequence 0.25 against 0.76.  seq_table:
+    // 0 = never, 1 = where runs average below 14 steps (default), 2 = always.  The launchers drop the table
+    // again where its strips do not fit (launch.hpp).
+    const long tab = g_seq_table.load();
+    sp.table_stride = (P == 0 && (tab >= 2 || (tab == 1 && L < 14u * sp.n_runs))) ? (L | 1u) : 0u;
     sp.settle_head = settle % L;
     sp.settle_periods = settle / L;
     sp.accum_periods = accum / L;

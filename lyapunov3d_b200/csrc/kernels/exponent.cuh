@@ -19,10 +19,10 @@
 //           per-symbol counts.  4 FP32 per step, no MUFU in the loop: FP32-bound.
 //   kHost   IEEE adds of a glibc-exact logf per step (reference host build).
 //
-// Sequence.  The symbol sequence is warp-uniform.  For a period P <= 32 the
+// Sequence.  The symbol sequence is warp-uniform.  For a period P <= 32 (and 36, 40) the
 // per-position multipliers live in P registers and the period is fully
-// unrolled (template parameter P); anything else takes the generic loop that
-// selects the multiplier per step (P == 0).
+// unrolled (template parameter P); anything else takes the generic path (P == 0):
+// a per-lane multiplier table in shared memory, or a run-length loop.
 #pragma once
 #include "arith.cuh"
 #include "hostlog.cuh"
@@ -30,7 +30,7 @@
 namespace lyap {
 
 constexpr int kMaxSeq = 1024;       // symbols per period accepted by the ABI
-constexpr int kMaxPeriodRegs = 32;  // longest period served by the register-table path
+constexpr int kMaxPeriodRegs = 40;  // longest period served by the register-table path
 
 enum Mode { kExact = 0, kFast = 1, kHost = 2 };
 

@@ -210,6 +210,18 @@ struct TailShared {
     RayState pool[96];      // repacking buffer: a repack happens only when the rays fit into <= 3 warps
 };
 
+// The "queue is empty" flag of a block: set by the first warp that sees the end of the queue, polled by the
+// others once per evaluation (a warp that reads a stale 0 just joins the protocol one evaluation later;
+// the barrier of the first round waits for it).  Shared-memory atomics, so that the set and the polls
+// are ordered accesses rather than a data race.
+__device__ __forceinline__ bool tail_flag_read(int *flag, unsigned lane)   // whole warp, converged
+{
+    int v = 0;
+    if (lane == 0) v = atomicOr(flag, 0);
+    return __shfl_sync(0xffffffffu, v, 0) != 0;
+}
+__device__ __forceinline__ void tail_flag_set(int *flag) { atomicExch(flag, 1); }
+
 __device__ __forceinline__ void block_barrier(int warps)
 {
     asm volatile("bar.sync 1, %0;" ::"r"(warps * 32) : "memory");
@@ -260,13 +272,13 @@ __global__ void __launch_bounds__(kRenderThreads, 4) render_kernel(const __grid_
     st.sx = st.sy = st.sz = 3.0f;   // idle lanes evaluate a harmless dummy point (not 2.0: that orbit is superstable)
     bool drained = false, announced = false, solo = false;
     int team = kRenderThreads / 32;   // warps of the block still taking part in the tail protocol
-    unsigned it = 0;
+    unsigned it = 0, poll = 0;
     unsigned long long evals = 0;
     // hybrid mode's second launch: the rays are the ones the march kernel listed
     const unsigned long long n_items = a.worklist ? *a.work_count : a.n_items;
 
     for (;;) {
-        if (!drained && *reinterpret_cast<volatile int *>(&ts.drained)) drained = true;
+        if (!drained && (poll++ & 3u) == 0 && tail_flag_read(&ts.drained, lane)) drained = true;   // every 4th evaluation: the atomic poll costs ~0.6 % otherwise
         // ---- refill idle lanes from the queue
         for (;;) {
             const bool need = st.phase == kNeedRay;
@@ -300,7 +312,7 @@ __global__ void __launch_bounds__(kRenderThreads, 4) render_kernel(const __grid_
             // ---- tail protocol: every warp of the team gets here once per evaluation
             if (!announced) {
                 announced = true;
-                if (lane == 0) *reinterpret_cast<volatile int *>(&ts.drained) = 1;
+                if (lane == 0) tail_flag_set(&ts.drained);
             }
             const unsigned buf = it++ & 1u;
             if (lane == 0) ts.cnt[buf][warp] = __popc(live_mask);
@@ -401,7 +413,7 @@ __device__ __forceinline__ bool tail_turn(TailPool<State, SLOTS> &ts, TailCtl &c
     if (!c.drained) return true;
     if (!c.announced) {
         c.announced = true;
-        if (lane == 0) *reinterpret_cast<volatile int *>(&ts.drained) = 1;
+        if (lane == 0) tail_flag_set(&ts.drained);
     }
     const unsigned buf = c.it++ & 1u;
     if (lane == 0) ts.cnt[buf][warp] = mine;
@@ -464,10 +476,11 @@ __global__ void __launch_bounds__(kRenderThreads, 3) render_fast2_kernel(const _
     }
     TailCtl tc;
     bool &drained = tc.drained;
+    unsigned poll = 0;
     unsigned long long evals = 0;
 
     for (;;) {
-        if (!drained && *reinterpret_cast<volatile int *>(&ts.drained)) drained = true;
+        if (!drained && (poll++ & 3u) == 0 && tail_flag_read(&ts.drained, lane)) drained = true;   // every 4th evaluation: the atomic poll costs ~0.6 % otherwise
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             for (;;) {
@@ -562,6 +575,7 @@ __global__ void __launch_bounds__(kRenderThreads, 3) march_fast2_kernel(const __
     }
     TailCtl tc;
     bool &drained = tc.drained;
+    unsigned poll = 0;
     unsigned long long evals = 0, skipped = 0;
 
     auto out_of = [&](uint32_t item) {
@@ -620,7 +634,7 @@ __global__ void __launch_bounds__(kRenderThreads, 3) march_fast2_kernel(const __
     };
 
     for (;;) {
-        if (!drained && *reinterpret_cast<volatile int *>(&ts.drained)) drained = true;
+        if (!drained && (poll++ & 3u) == 0 && tail_flag_read(&ts.drained, lane)) drained = true;   // every 4th evaluation: the atomic poll costs ~0.6 % otherwise
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             for (;;) {

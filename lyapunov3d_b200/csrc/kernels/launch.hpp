@@ -5,11 +5,13 @@
 
 #include "kernels.cuh"
 
-// Sequence periods with a register-table instantiation: every period up to 32 symbols.
-// Longer periods use the run-length loop (0).
+// Sequence periods with a register-table instantiation: every period up to 32 symbols, plus 36 and 40
+// (A8B8C8D8, A9B9C9D9: the register table still fits; 48 spills).  Other periods take the generic path (0):
+// a per-lane multiplier table in shared memory, or the run-length loop where that does not fit.
 #define LYAP_PERIODS(X) \
     X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) \
-    X(17) X(18) X(19) X(20) X(21) X(22) X(23) X(24) X(25) X(26) X(27) X(28) X(29) X(30) X(31) X(32)
+    X(17) X(18) X(19) X(20) X(21) X(22) X(23) X(24) X(25) X(26) X(27) X(28) X(29) X(30) X(31) X(32) \
+    X(36) X(40)
 
 namespace lyap {
 
@@ -34,10 +36,13 @@ inline size_t settle_seq_table(int mode, Args &a, size_t entry_bytes, size_t thr
     }
     return bytes;
 }
+// The opt-in limit of a kernel is a constant per (mode, period) -- the most any launch of it may ask
+// for -- so that concurrent launches from several host threads never lower it under each other.
+constexpr size_t dyn_smem_cap(int mode, int P) { return dyn_smem_of(mode) + ((P == 0 && mode != kHost) ? kSeqTableMaxBytes : 0); }
 template <class K>
-inline void opt_in_dyn_smem(K kernel, size_t bytes)
+inline void opt_in_dyn_smem(K kernel, size_t cap)
 {
-    if (bytes) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (cap) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
 }
 
 #define LYAP_DECLARE_MODE(NAME)                                                                          \

@@ -22,7 +22,7 @@ cudaError_t LYAP_CAT(launch_bake_, LYAP_TU_NAME)(int P, const BakeArgs &args, un
     const unsigned threads = P == 0 ? (unsigned)LYAP_CAT(bake_threads_, LYAP_TU_NAME)(a.plan) : 256u;
     const size_t dyn = dyn_smem_of(LYAP_TU_MODE) + (P == 0 ? settle_seq_table(LYAP_TU_MODE, a, kBakeEntry, threads) : 0);
     switch (P) {
-#define X(p) case p: opt_in_dyn_smem(bake_kernel<LYAP_TU_MODE, p>, dyn); bake_kernel<LYAP_TU_MODE, p><<<grid, threads, dyn, s>>>(a); break;
+#define X(p) case p: opt_in_dyn_smem(bake_kernel<LYAP_TU_MODE, p>, dyn_smem_cap(LYAP_TU_MODE, p)); bake_kernel<LYAP_TU_MODE, p><<<grid, threads, dyn, s>>>(a); break;
         LYAP_PERIODS(X)
 #undef X
     default: return cudaErrorInvalidValue;
@@ -37,7 +37,7 @@ cudaError_t LYAP_CAT(launch_points_, LYAP_TU_NAME)(int P, const PointsArgs &args
     const unsigned threads = (tb != 0 && tb <= kSeqTableMaxBytes) ? 128u : 256u;
     const size_t dyn = dyn_smem_of(LYAP_TU_MODE) + (P == 0 ? settle_seq_table(LYAP_TU_MODE, a, 4, threads) : 0);
     switch (P) {
-#define X(p) case p: opt_in_dyn_smem(points_kernel<LYAP_TU_MODE, p>, dyn); points_kernel<LYAP_TU_MODE, p><<<grid, threads, dyn, s>>>(a); break;
+#define X(p) case p: opt_in_dyn_smem(points_kernel<LYAP_TU_MODE, p>, dyn_smem_cap(LYAP_TU_MODE, p)); points_kernel<LYAP_TU_MODE, p><<<grid, threads, dyn, s>>>(a); break;
         LYAP_PERIODS(X)
 #undef X
     default: return cudaErrorInvalidValue;
@@ -52,7 +52,7 @@ int LYAP_CAT(bake_blocks_per_sm_, LYAP_TU_NAME)(int P, const SeqPlan &plan)
     size_t dyn = dyn_smem_of(LYAP_TU_MODE);
     if (P == 0 && threads == 128) dyn += seq_table_bytes(LYAP_TU_MODE, plan, kBakeEntry, 128);
     switch (P) {
-#define X(p) case p: opt_in_dyn_smem(bake_kernel<LYAP_TU_MODE, p>, dyn); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, bake_kernel<LYAP_TU_MODE, p>, threads, dyn); break;
+#define X(p) case p: opt_in_dyn_smem(bake_kernel<LYAP_TU_MODE, p>, dyn_smem_cap(LYAP_TU_MODE, p)); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, bake_kernel<LYAP_TU_MODE, p>, threads, dyn); break;
         LYAP_PERIODS(X)
 #undef X
     default: break;

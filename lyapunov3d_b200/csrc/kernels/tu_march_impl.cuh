@@ -15,7 +15,7 @@ cudaError_t LYAP_CAT(launch_march_, LYAP_TU_NAME)(int P, const RenderArgs &args,
     if (LYAP_TU_MODE == kHost) a.plan.table_stride = 0;
     const size_t dyn = dyn_smem_of(LYAP_TU_MODE) + (P == 0 ? settle_seq_table(LYAP_TU_MODE, a, 8, kRenderThreads) : 0);
     switch (P) {
-#define X(p) case p: opt_in_dyn_smem(march_fast2_kernel<LYAP_TU_MODE, p>, dyn); march_fast2_kernel<LYAP_TU_MODE, p><<<grid, kRenderThreads, dyn, s>>>(a); break;
+#define X(p) case p: opt_in_dyn_smem(march_fast2_kernel<LYAP_TU_MODE, p>, dyn_smem_cap(LYAP_TU_MODE, p)); march_fast2_kernel<LYAP_TU_MODE, p><<<grid, kRenderThreads, dyn, s>>>(a); break;
         LYAP_PERIODS(X)
 #undef X
     default: return cudaErrorInvalidValue;
@@ -29,7 +29,7 @@ int LYAP_CAT(march_blocks_per_sm_, LYAP_TU_NAME)(int P, const SeqPlan &plan)
     size_t dyn = dyn_smem_of(LYAP_TU_MODE);
     if (P == 0 && seq_table_bytes(LYAP_TU_MODE, plan, 8, kRenderThreads) <= kSeqTableMaxBytes) dyn += seq_table_bytes(LYAP_TU_MODE, plan, 8, kRenderThreads);
     switch (P) {
-#define X(p) case p: opt_in_dyn_smem(march_fast2_kernel<LYAP_TU_MODE, p>, dyn); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, march_fast2_kernel<LYAP_TU_MODE, p>, kRenderThreads, dyn); break;
+#define X(p) case p: opt_in_dyn_smem(march_fast2_kernel<LYAP_TU_MODE, p>, dyn_smem_cap(LYAP_TU_MODE, p)); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, march_fast2_kernel<LYAP_TU_MODE, p>, kRenderThreads, dyn); break;
         LYAP_PERIODS(X)
 #undef X
     default: break;

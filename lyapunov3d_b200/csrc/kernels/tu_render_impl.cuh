@@ -24,7 +24,7 @@ cudaError_t LYAP_CAT(launch_render_, LYAP_TU_NAME)(int P, const RenderArgs &args
     RenderArgs a = args;
     const size_t dyn = dyn_smem_of(LYAP_TU_MODE) + (P == 0 ? settle_seq_table(LYAP_TU_MODE, a, kRenderEntry, kRenderThreads) : 0);
     switch (P) {
-#define X(p) case p: opt_in_dyn_smem(LYAP_RENDER_KERNEL(p), dyn); LYAP_RENDER_KERNEL(p)<<<grid, kRenderThreads, dyn, s>>>(a); break;
+#define X(p) case p: opt_in_dyn_smem(LYAP_RENDER_KERNEL(p), dyn_smem_cap(LYAP_TU_MODE, p)); LYAP_RENDER_KERNEL(p)<<<grid, kRenderThreads, dyn, s>>>(a); break;
         LYAP_PERIODS(X)
 #undef X
     default: return cudaErrorInvalidValue;
@@ -39,7 +39,7 @@ int LYAP_CAT(render_blocks_per_sm_, LYAP_TU_NAME)(int P, const SeqPlan &plan)
     if (P == 0 && seq_table_bytes(LYAP_TU_MODE, plan, kRenderEntry, kRenderThreads) <= kSeqTableMaxBytes)
         dyn += seq_table_bytes(LYAP_TU_MODE, plan, kRenderEntry, kRenderThreads);
     switch (P) {
-#define X(p) case p: opt_in_dyn_smem(LYAP_RENDER_KERNEL(p), dyn); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, LYAP_RENDER_KERNEL(p), kRenderThreads, dyn); break;
+#define X(p) case p: opt_in_dyn_smem(LYAP_RENDER_KERNEL(p), dyn_smem_cap(LYAP_TU_MODE, p)); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, LYAP_RENDER_KERNEL(p), kRenderThreads, dyn); break;
         LYAP_PERIODS(X)
 #undef X
     default: break;

@@ -133,14 +133,14 @@ def test_generic_sequence_loop_equals_unrolled_periods(scene, mode):
     a = lp.bake(prm, seq, 24, 16, 8, mode=mode).cpu().numpy()
     api.set_option("force_generic", 1)
     try:
-        for table in (1, 0):             # shared-memory multiplier table, run-length loop
+        for table in (2, 0):             # shared-memory multiplier table (forced), run-length loop
             api.set_option("seq_table", table)
             b = lp.bake(prm, seq, 24, 16, 8, mode=mode).cpu().numpy()
             if mode == "fast":
                 assert close_nan(a, b, 2e-5), table     # the fold cadence differs, the value is the same
             else:
                 assert same_floats(a, b), table
-        long_seq = lp.scene_convert_sequence("A9B9C9D9")           # 40 symbols: always generic
+        long_seq = lp.scene_convert_sequence("A9A8B9B9")           # 39 symbols: always generic
         assert api.plan_period(long_seq, 18, 1008) == 0
     finally:
         api.set_option("force_generic", 0)
@@ -149,13 +149,13 @@ def test_generic_sequence_loop_equals_unrolled_periods(scene, mode):
 
 def test_long_period_table_path_equals_run_length_loop(scene):
     """Periods above 32 symbols: the per-lane multiplier table in shared memory (default) against the
-    run-length loop (seq_table = 0) -- bake, points and frames, with settle counts that are not
+    run-length loop (seq_table = 2 / 0) -- bake, points and frames, with settle counts that are not
     multiples of the period, and periods whose table no longer fits (the launcher falls back)."""
     prm0, cam, lights, n, _ = scene
     c = clone(cam)
     lp.scene_cam_recalculate(c, 48, 32, 1)
     rng = np.random.default_rng(5)
-    seqs = ["A9B9C9D9", "A9A8B9B9", "ABCDABCDABCDABCDABCDABCDABCDABCDABCDA",
+    seqs = ["A9B9C9D9B3", "A9A8B9B9", "ABCDABCDABCDABCDABCDABCDABCDABCDABCDA",
             "".join("ABC"[i] for i in rng.integers(0, 3, 53)),        # 53: fits as 4-byte entries and as pairs
             "".join("ABC"[i] for i in rng.integers(0, 3, 97)),        # 97: fits as 4-byte entries only
             "".join("AB"[i] for i in rng.integers(0, 2, 301))]        # 301: never fits
@@ -168,7 +168,7 @@ def test_long_period_table_path_equals_run_length_loop(scene):
                 prm.settle, prm.accum, prm.d = settle, accum, 3.2
                 assert api.plan_period(seq, settle, accum) == 0
                 got = {}
-                for table in (1, 0):
+                for table in (2, 0):          # 2: the table wherever it fits, 0: never (default 1: by run length)
                     api.set_option("seq_table", table)
                     got[table] = dict(
                         be=lp.bake(prm, seq, 20, 10, 6, mode="exact").cpu().numpy(),
@@ -182,7 +182,7 @@ def test_long_period_table_path_equals_run_length_loop(scene):
                         got[table]["rf"] = lp.render(c, prm, seq, lights, n, 48, 32, mode="fast")
                         got[table]["rh"] = lp.render(c, pj, seq, lights, n, 48, 32, mode="hybrid")
                         got[table]["rp"] = lp.render(c, pj, seq, lights, n, 48, 32, mode="exact")
-                t, r = got[1], got[0]
+                t, r = got[2], got[0]
                 assert same_floats(t["be"], r["be"]) and same_floats(t["pe"], r["pe"]), (len(s_txt), settle)
                 assert close_nan(t["bf"], r["bf"], 2e-5) and close_nan(t["pf"], r["pf"], 2e-5), (len(s_txt), settle)
                 if accum == 333:
@@ -205,13 +205,14 @@ def test_long_period_table_path_equals_run_length_loop(scene):
 
 
 def test_long_sequence_against_oracle(oracle, scene):
-    """Sequences longer than 32 symbols take the run-length loop (40, 39 and 44 symbols; the last
+    """Sequences longer than 32 symbols: 40 has a register-table instantiation, the others (39, 44, 37
+    symbols) take the generic path -- shared-memory table in fast / exact mode, run-length loop in host mode (the last
     one starts with a run of one)."""
     prm = clone(scene[0])
     prm.d = 3.2
     for s in ("A9B9C9D9", "A9A8B9B9", "ABBBBBBBBBBBBBBBBBBBBBBBBBBBBBBBBBBBBBBBBBBB", "ABCDABCDABCDABCDABCDABCDABCDABCDABCDA"):
         seq = lp.scene_convert_sequence(s)
-        assert api.plan_period(seq, prm.settle, prm.accum) == 0
+        assert api.plan_period(seq, prm.settle, prm.accum) == (40 if s == "A9B9C9D9" else 0)
         want = oracle.bake(prm, seq, 12, 10, 6)
         assert same_floats(lp.bake(prm, seq, 12, 10, 6, mode="host").cpu().numpy(), want)
         assert close_nan(lp.bake(prm, seq, 12, 10, 6, mode="fast").cpu().numpy(), want, BAKE_TOL)
@@ -895,7 +896,7 @@ def test_every_period_instantiation_and_odd_iteration_counts(oracle, scene):
     not multiples of the period (rotation, partial head and tail periods), a D symbol and d != default."""
     rng = np.random.default_rng(5)
     prm = clone(scene[0])
-    for period in list(range(1, 33)) + [33, 47]:
+    for period in list(range(1, 33)) + [33, 36, 40, 47]:
         while True:
             body = rng.integers(0, 4, period)
             if period == 1 or not any(period % p == 0 and (body == np.tile(body[:p], period // p)).all() for p in range(1, period)):
@@ -904,7 +905,7 @@ def test_every_period_instantiation_and_odd_iteration_counts(oracle, scene):
         prm.settle = int(rng.integers(0, 3 * period + 2))
         prm.accum = int(rng.integers(1, 5 * period + 40))
         prm.d = float(np.float32(rng.uniform(2.5, 3.9)))
-        assert api.plan_period(seq, prm.settle, prm.accum) == (period if period <= 32 else 0)
+        assert api.plan_period(seq, prm.settle, prm.accum) == (period if period <= 32 or period in (36, 40) else 0)
         want = oracle.bake(prm, seq, 8, 4, 4)
         got = lp.bake(prm, seq, 8, 4, 4, mode="host").cpu().numpy()
         assert same_floats(got, want), (period, prm.settle, prm.accum)

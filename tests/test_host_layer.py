@@ -84,9 +84,10 @@ def test_plan_picks_period_instantiations():
     assert api.plan_period(conv("A6B6C6"), 72, 4032) == 21
     assert api.plan_period(conv("ABAB"), 18, 1008) == 2          # reduced to its true period
     assert api.plan_period(conv("A8B8"), 18, 1008) == 18
-    assert api.plan_period(conv("A9B9C9D9"), 18, 1008) == 0      # 40 symbols: generic loop
+    assert api.plan_period(conv("A9B9C9D9"), 18, 1008) == 40     # 36 and 40 symbols still have a register table
+    assert api.plan_period(conv("A9B9C9D9B3"), 18, 1008) == 0    # 44 symbols: generic path
     assert api.plan_period(conv("A8B7"), 18, 1008) == 17         # every period up to 32 has an instantiation
-    assert api.plan_period(conv("A9A8B9B9"), 18, 1008) == 0      # 39 symbols: run-length loop
+    assert api.plan_period(conv("A9A8B9B9"), 18, 1008) == 0      # 39 symbols: generic path
     assert api.plan_period(np.array([0, 5, -1], np.int32), 1, 1) == -1
     assert api.plan_period(np.array([-1], np.int32), 1, 1) == -1
     assert api.tile_count(1920, 1080, 8, 0, 1) == 240 * 135 * 64

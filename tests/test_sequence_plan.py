@@ -45,7 +45,7 @@ def test_plan_generates_the_reference_symbol_stream(s, settle, accum):
     assert stream_from_runs(d, settle + accum) == want                 # run-length form, any length
     assert sum(ln for _, ln in d["runs"]) == d["len"] and all(1 <= ln <= 255 for _, ln in d["runs"])
     if d["P"] > 0:
-        assert d["len"] == d["P"] <= 32
+        assert d["len"] == d["P"] <= 40
         assert stream_from_table(d, settle, accum) == want              # register-table form
     census = [want[settle:].count(k) for k in range(4)]
     assert d["cnt"] == census                                           # fast mode's analytic sum(log r)

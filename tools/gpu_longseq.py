@@ -13,7 +13,7 @@ peaks = api.probe_peaks()
 it = prm.settle + prm.accum
 peak = {"exact": peaks["mufu_lane_ops_per_s"] / (prm.accum / it), "fast": peaks["ffma_lane_ops_per_s"] / ((2.0 * prm.settle + 4.0 * prm.accum) / it)}
 rng = np.random.default_rng(5)
-seqs = {"BCABA (register table, for reference)": "BCABA", "A9B9C9D9": "A9B9C9D9", "random53": "".join("ABC"[i] for i in rng.integers(0, 3, 53))}
+seqs = {"BCABA (register table, for reference)": "BCABA", "A9B9C9D9 (register table P=40)": "A9B9C9D9", "A9A8B9B9 (39 symbols)": "A9A8B9B9", "random53": "".join("ABC"[i] for i in rng.integers(0, 3, 53))}
 def timed(fn, reps=3):
     fn(); torch.cuda.synchronize(); best = 1e9
     for _ in range(reps):

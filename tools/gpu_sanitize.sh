@@ -9,9 +9,12 @@ import torch, lyapunov3d_b200 as lp
 from lyapunov3d_b200 import api
 from lyapunov3d_b200.structs import clone
 prm, cam, lights, n, s, _ = lp.params_init(); lp.scene_lights_recalculate(lights, n)
-prm.accum = 120
+prm.accum = 80
 launches = 0
-for sq in ("BCABA", "A6B6C6", "A9B9C9D9"):
+# (sequence, seq_table): register-table periods 5, 21, 40; generic path with the shared-memory
+# multiplier table forced (2) and with the run-length loop (0)
+for sq, table in (("BCABA", 1), ("A9B9C9D9", 1), ("A9A8B9B9", 2), ("A9A8B9B9", 0), ("ABCABBCACABBACBCAABCABCCBACBABCABACBBCA", 2)):
+    api.set_option("seq_table", table)
     seq = lp.scene_convert_sequence(sq)
     c = clone(cam); lp.scene_cam_recalculate(c, 37, 21, 1)
     for mode in ("exact", "fast", "host"):
