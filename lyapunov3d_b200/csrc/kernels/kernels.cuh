@@ -205,22 +205,20 @@ __device__ __forceinline__ void finish_pixel(const RenderArgs &a, const RayState
 // leaves the survivors of co-resident blocks on different schedulers (tail_rank); the emptied warps exit.  Rays are independent and their state is moved verbatim: results do not change.
 struct TailShared {
     unsigned rank_tab[4];   // see tail_rank()
-    int drained;            // some warp of the block saw the end of the queue
     int cnt[2][4];          // live rays per warp, double-buffered by iteration parity
     RayState pool[96];      // repacking buffer: a repack happens only when the rays fit into <= 3 warps
 };
 
-// The "queue is empty" flag of a block: set by the first warp that sees the end of the queue, polled by the
-// others once per evaluation (a warp that reads a stale 0 just joins the protocol one evaluation later;
-// the barrier of the first round waits for it).  Shared-memory atomics, so that the set and the polls
-// are ordered accesses rather than a data race.
-__device__ __forceinline__ bool tail_flag_read(int *flag, unsigned lane)   // whole warp, converged
+// How a warp that needs no ray learns that the queue is empty (it must then join its block's tail
+// protocol): it looks at the queue head itself once per evaluation.  The load is issued before the
+// evaluation and its value looked at after it, ~4 us later, so it costs no stall; the head only grows,
+// so a stale value just means joining one evaluation later (the first barrier of the protocol waits).
+__device__ __forceinline__ unsigned long long queue_peek(const unsigned long long *queue)
 {
-    int v = 0;
-    if (lane == 0) v = atomicOr(flag, 0);
-    return __shfl_sync(0xffffffffu, v, 0) != 0;
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(queue));
+    return v;
 }
-__device__ __forceinline__ void tail_flag_set(int *flag) { atomicExch(flag, 1); }
 
 __device__ __forceinline__ void block_barrier(int warps)
 {
@@ -260,7 +258,6 @@ __global__ void __launch_bounds__(kRenderThreads, 4) render_kernel(const __grid_
 {
     using A = typename ArithOf<MODE>::type;
     __shared__ TailShared ts;
-    if (threadIdx.x == 0) ts.drained = 0;
     if constexpr (MODE == kHost) hostlog_init();
 
     const unsigned full = 0xffffffffu;
@@ -270,15 +267,15 @@ __global__ void __launch_bounds__(kRenderThreads, 4) render_kernel(const __grid_
     RayState st;
     st.phase = kNeedRay;
     st.sx = st.sy = st.sz = 3.0f;   // idle lanes evaluate a harmless dummy point (not 2.0: that orbit is superstable)
-    bool drained = false, announced = false, solo = false;
+    bool drained = false, solo = false;
     int team = kRenderThreads / 32;   // warps of the block still taking part in the tail protocol
-    unsigned it = 0, poll = 0;
-    unsigned long long evals = 0;
+    unsigned it = 0;
+    unsigned long long evals = 0, head = 0;   // head: the queue head as of the previous evaluation
     // hybrid mode's second launch: the rays are the ones the march kernel listed
     const unsigned long long n_items = a.worklist ? *a.work_count : a.n_items;
 
     for (;;) {
-        if (!drained && (poll++ & 3u) == 0 && tail_flag_read(&ts.drained, lane)) drained = true;   // every 4th evaluation: the atomic poll costs ~0.6 % otherwise
+        if (head >= n_items) drained = true;
         // ---- refill idle lanes from the queue
         for (;;) {
             const bool need = st.phase == kNeedRay;
@@ -310,10 +307,6 @@ __global__ void __launch_bounds__(kRenderThreads, 4) render_kernel(const __grid_
             if (live_mask == 0 && drained) break;
         } else if (drained) {
             // ---- tail protocol: every warp of the team gets here once per evaluation
-            if (!announced) {
-                announced = true;
-                if (lane == 0) tail_flag_set(&ts.drained);
-            }
             const unsigned buf = it++ & 1u;
             if (lane == 0) ts.cnt[buf][warp] = __popc(live_mask);
             block_barrier(team);
@@ -349,6 +342,7 @@ __global__ void __launch_bounds__(kRenderThreads, 4) render_kernel(const __grid_
         }
 
         // ---- one exponent for every lane (idle lanes evaluate a dummy point)
+        if (!drained) head = queue_peek(a.queue);
         const float l = exponent<MODE, P>(a.plan, st.sx, st.sy, st.sz, a.prm.d);
 
         // ---- advance each ray by that one sample
@@ -383,15 +377,15 @@ __global__ void __launch_bounds__(kRenderThreads, 4) render_kernel(const __grid_
 template <class State, int SLOTS>
 struct TailPool {
     unsigned rank_tab[4];
-    int drained;
     int cnt[2][4];
     State pool[96 * SLOTS];
 };
 
 struct TailCtl {
-    bool drained = false, announced = false, solo = false;
+    bool drained = false, solo = false;
     int team = kRenderThreads / 32;
     unsigned it = 0;
+    unsigned long long head = 0;   // the queue head as of the previous evaluation (queue_peek)
 };
 
 // One turn of the protocol, called after the refill of every iteration.  live[j]: slot j holds a ray.
@@ -411,10 +405,6 @@ __device__ __forceinline__ bool tail_turn(TailPool<State, SLOTS> &ts, TailCtl &c
     }
     if (c.solo || !enabled) return !(mine == 0 && c.drained);
     if (!c.drained) return true;
-    if (!c.announced) {
-        c.announced = true;
-        if (lane == 0) tail_flag_set(&ts.drained);
-    }
     const unsigned buf = c.it++ & 1u;
     if (lane == 0) ts.cnt[buf][warp] = mine;
     block_barrier(c.team);
@@ -463,7 +453,6 @@ __global__ void __launch_bounds__(kRenderThreads, 3) render_fast2_kernel(const _
 {
     using A = ArithDev;
     __shared__ TailPool<RayState, 2> ts;
-    if (threadIdx.x == 0) ts.drained = 0;
     const unsigned full = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31;
     const unsigned warp = threadIdx.x >> 5;
@@ -476,11 +465,10 @@ __global__ void __launch_bounds__(kRenderThreads, 3) render_fast2_kernel(const _
     }
     TailCtl tc;
     bool &drained = tc.drained;
-    unsigned poll = 0;
     unsigned long long evals = 0;
 
     for (;;) {
-        if (!drained && (poll++ & 3u) == 0 && tail_flag_read(&ts.drained, lane)) drained = true;   // every 4th evaluation: the atomic poll costs ~0.6 % otherwise
+        if (tc.head >= a.n_items) drained = true;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             for (;;) {
@@ -511,6 +499,7 @@ __global__ void __launch_bounds__(kRenderThreads, 3) render_fast2_kernel(const _
             break;
 
         float l[2];
+        if (!drained) tc.head = queue_peek(a.queue);
         exponent_fast2<P>(a.plan, st[0].sx, st[0].sy, st[0].sz, st[1].sx, st[1].sy, st[1].sz, a.prm.d, l[0], l[1]);
 
 #pragma unroll
@@ -561,7 +550,6 @@ __global__ void __launch_bounds__(kRenderThreads, 3) march_fast2_kernel(const __
 {
     using A = typename ArithOf<MODE>::type;
     __shared__ TailPool<MarchState, 2> ts;
-    if (threadIdx.x == 0) ts.drained = 0;
     if constexpr (MODE == kHost) hostlog_init();
     const unsigned full = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31;
@@ -575,7 +563,6 @@ __global__ void __launch_bounds__(kRenderThreads, 3) march_fast2_kernel(const __
     }
     TailCtl tc;
     bool &drained = tc.drained;
-    unsigned poll = 0;
     unsigned long long evals = 0, skipped = 0;
 
     auto out_of = [&](uint32_t item) {
@@ -634,7 +621,7 @@ __global__ void __launch_bounds__(kRenderThreads, 3) march_fast2_kernel(const __
     };
 
     for (;;) {
-        if (!drained && (poll++ & 3u) == 0 && tail_flag_read(&ts.drained, lane)) drained = true;   // every 4th evaluation: the atomic poll costs ~0.6 % otherwise
+        if (tc.head >= a.n_items) drained = true;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             for (;;) {
@@ -675,6 +662,7 @@ __global__ void __launch_bounds__(kRenderThreads, 3) march_fast2_kernel(const __
         const unsigned parked = __popc(__ballot_sync(full, park0 || park1));
         if (!any_fast && parked == 0) continue;   // (only before the queue is known to be empty; the tail protocol ends the loop)
 
+        if (!drained) tc.head = queue_peek(a.queue);
         if (any_fast && parked < a.guard_batch) {
             // a parked slot sits the fast pass out on the dummy point: its own sample may well be a
             // zero-derivative one (NaN parks too), which would drag the warp through the fast
