@@ -294,6 +294,9 @@ static __device__ __noinline__ float fast_redo(const SeqPlan &sp, float x, float
 template <int P>
 struct PeriodUnroll {
     static constexpr int U = (P >= 11) ? 1 : (20 / (P > 0 ? P : 1));  // periods per loop body
+    // packed fast evaluator: ~40-step bodies (two folds), which halves the loop control and the register
+    // moves the compiler needs to close a body (3 of the 16 non-FMA instructions per 20 steps)
+    static constexpr int U2 = (P >= 21) ? 1 : (40 / (P > 0 ? P : 1));
 };
 
 // `strip_entry`: bytes per entry of the calling kernel's per-lane strips in the generic path's multiplier
@@ -438,15 +441,23 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
 
 struct AccumFast2 {
     static constexpr int kBias = Accum<kFast>::kBias;
+    // Folds of the unrolled-period loops (renorm_pos) cost three integer instructions per sample:
+    // the step before the fold multiplies with |prod| * |q| (two scalar FMULs with source modifiers
+    // in place of one FMUL2: the same two issue cycles), so prod has no sign bit at the fold and
+    //   esum += bits >> 23          one LEA.HI; the bias is taken off once at the end (nfold of them)
+    //   emin  = min(emin, bits)     raw bits: an exponent field of zero <=> emin < 2^23
+    //   prod  = (bits & mantissa) | bias
+    // The sign-agnostic renorm() (five instructions) serves the remainder loops and the generic paths.
     f32x2 prod;
-    int esum0, esum1, emin0, emin1, bias_bits;
+    int esum0, esum1, emin0, emin1, bias_bits, nfold;
     __device__ __forceinline__ void init(uint32_t fold_bias)
     {
         bias_bits = (int)fold_bias;
         const float b = __int_as_float((127 + kBias) << 23);
         prod = pack2(b, b);
         esum0 = esum1 = 0;
-        emin0 = emin1 = 255;
+        emin0 = emin1 = 0x7fffffff;
+        nfold = 0;
     }
     __device__ __forceinline__ void step(f32x2 r, f32x2 &w, f32x2 two, f32x2 one)
     {
@@ -454,17 +465,46 @@ struct AccumFast2 {
         w = fma2(p, w, p);
         prod = mul2(prod, fma2(two, w, one));
     }
-    __device__ __forceinline__ void renorm()
+    // the step before a renorm_pos(): leaves prod >= 0
+    __device__ __forceinline__ void step_abs(f32x2 r, f32x2 &w, f32x2 two, f32x2 one)
+    {
+        const f32x2 p = mul2(r, w);
+        w = fma2(p, w, p);
+        float pa, pb, qa, qb;
+        unpack2(prod, pa, pb);
+        unpack2(fma2(two, w, one), qa, qb);
+        prod = pack2(__fmul_rn(fabsf(pa), fabsf(qa)), __fmul_rn(fabsf(pb), fabsf(qb)));
+    }
+    __device__ __forceinline__ void renorm_pos()
     {
         float a, b;
         unpack2(prod, a, b);
         const int ba = __float_as_int(a), bb = __float_as_int(b);
-        const int ea = (ba >> 23) & 0xff, eb = (bb >> 23) & 0xff;   // the sign of prod is not tracked: drop it
-        esum0 += ea - (127 + kBias);
-        esum1 += eb - (127 + kBias);
-        emin0 = min(emin0, ea);
-        emin1 = min(emin1, eb);
+        esum0 += (int)((unsigned)ba >> 23);
+        esum1 += (int)((unsigned)bb >> 23);
+        emin0 = min(emin0, ba);
+        emin1 = min(emin1, bb);
+        nfold += 1;
         prod = pack2(__int_as_float((ba & 0x007fffff) | bias_bits), __int_as_float((bb & 0x007fffff) | bias_bits));
+    }
+    __device__ __forceinline__ void renorm()
+    {
+        float a, b;
+        unpack2(prod, a, b);
+        const int ba = __float_as_int(a) & 0x7fffffff, bb = __float_as_int(b) & 0x7fffffff;   // the sign of prod is not tracked: drop it
+        esum0 += (ba >> 23) - (127 + kBias);
+        esum1 += (bb >> 23) - (127 + kBias);
+        emin0 = min(emin0, ba);
+        emin1 = min(emin1, bb);
+        prod = pack2(__int_as_float((ba & 0x007fffff) | bias_bits), __int_as_float((bb & 0x007fffff) | bias_bits));
+    }
+    // after the last fold: the biases of the renorm_pos() folds come off, emin becomes an exponent field
+    __device__ __forceinline__ void close()
+    {
+        esum0 -= nfold * (127 + kBias);
+        esum1 -= nfold * (127 + kBias);
+        emin0 >>= 23;
+        emin1 >>= 23;
     }
 };
 
@@ -533,14 +573,18 @@ __device__ __forceinline__ void exponent_fast2(const SeqPlan &sp, float xa, floa
             for (int k = 0; k < P; k++) settle_step(r[k]);
         }
         unpack2(w, vsa, vsb);
-        constexpr int U = PeriodUnroll<P>::U;
+        constexpr int U = PeriodUnroll<P>::U2;
         const uint32_t groups = sp.accum_periods / U;
 #pragma unroll 1
         for (uint32_t g = 0; g < groups; g++) {
 #pragma unroll
             for (int s = 0; s < U * P; s++) {
-                acc.step(r[s % P], w, two, one);
-                if ((s + 1) % Accum<kFast>::kFoldEvery == 0 || s + 1 == U * P) acc.renorm();
+                if ((s + 1) % Accum<kFast>::kFoldEvery == 0 || s + 1 == U * P) {
+                    acc.step_abs(r[s % P], w, two, one);
+                    acc.renorm_pos();
+                } else {
+                    acc.step(r[s % P], w, two, one);
+                }
             }
         }
         if constexpr (U > 1) {
@@ -580,6 +624,7 @@ __device__ __forceinline__ void exponent_fast2(const SeqPlan &sp, float xa, floa
         run_steps(sp, cur, sp.accum, rpair, [&](f32x2 r) { acc.step(r, w, two, one); }, [&] { acc.renorm(); });
     }
     acc.renorm();
+    acc.close();
     float pa, pb, wa, wb;
     unpack2(acc.prod, pa, pb);
     unpack2(w, wa, wb);
