@@ -108,6 +108,8 @@ int build_plan(SeqPlan &sp, const int32_t *seq, uint32_t settle, uint32_t accum)
     for (uint32_t i = 0; i < L; ++i) per_period[sp.sym[i]]++;
     for (int s = 0; s < 4; ++s) sp.cnt[s] = per_period[s] * sp.accum_periods;
     for (uint32_t k = 0; k < sp.accum_tail; ++k) sp.cnt[sp.sym[(sp.settle_head + k) % L]]++;
+    for (int s = 0; s < 4; ++s) sp.cnt_d[s] = (double)sp.cnt[s];
+    sp.ln2_over_accum = 0.6931471805599453 / (double)accum;   // accum == 0: inf, and 0 * inf = NaN as before
     return P;
 }
 

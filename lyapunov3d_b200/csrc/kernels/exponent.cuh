@@ -31,11 +31,14 @@ namespace lyap {
 
 constexpr int kMaxSeq = 1024;       // symbols per period accepted by the ABI
 constexpr int kMaxPeriodRegs = 40;  // longest period served by the register-table path
+constexpr int kSymTabThreads = 256; // largest block that calls the packed evaluator (its per-thread multiplier columns)
 
 enum Mode { kExact = 0, kFast = 1, kHost = 2 };
 
 // Uniform description of the iteration schedule; lives in kernel parameter space.
 struct SeqPlan {
+    double ln2_over_accum;    // fast evaluator: ln 2 / accum (a warp-uniform double division otherwise paid per sample)
+    double cnt_d[4];          // cnt[] as doubles (likewise)
     uint32_t len;             // period in symbols
     uint32_t settle, accum;   // reference prm.settle / prm.accum
     uint32_t settle_head;     // settle % len: steps taken before the rotated periods start
@@ -280,7 +283,7 @@ struct Accum<kFast> {
         if (sp.cnt[1]) l2 += (double)sp.cnt[1] * (double)__log2f(fabsf(y));
         if (sp.cnt[2]) l2 += (double)sp.cnt[2] * (double)__log2f(fabsf(z));
         if (sp.cnt[3]) l2 += (double)sp.cnt[3] * (double)__log2f(fabsf(d));
-        float l = (float)(l2 * (0.6931471805599453 / (double)sp.accum));
+        float l = (float)(l2 * sp.ln2_over_accum);
         // zero derivative somewhere (log -> -inf) or an orbit that left [0,1] for good
         bool bad = (emin == 0) || !is_finite(v) || !is_finite(l);
         return bad ? quiet_nan() : l;
@@ -515,11 +518,18 @@ struct AccumFast2 {
 // A_i = sum log|1 - 2v| (every term <= 0: monotone, so A_i lies in [A, 0] for the final A the fast
 // evaluator holds) and B_i = sum log r over the symbols seen so far (between -Bneg and Bpos): hence
 // max |S_i| <= max(|A| + Bneg, Bpos).  The caller adds the parity evaluator's per-term error.
+__device__ __forceinline__ float lg2_ftz(float x)   // for normal x (a mantissa in [1,2)): no denormal pre-scaling
+{
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ float fast_finish(const SeqPlan &sp, int esum, int emin, float prod, float x, float y, float z,
                                              float d, float v, float *guard = nullptr)
 {
     const float mant = __int_as_float((__float_as_int(prod) & 0x007fffff) | 0x3f800000);
-    const float lgm = __log2f(mant);
+    const float lgm = lg2_ftz(mant);
     double l2 = (double)esum + (double)lgm;
     float bpos = 0.0f, bneg = 0.0f;   // float is plenty for the guard: only the binade of the bound matters
     const float r4[4] = {x, y, z, d};
@@ -527,7 +537,7 @@ __device__ __forceinline__ float fast_finish(const SeqPlan &sp, int esum, int em
     for (int k = 0; k < 4; ++k) {
         if (sp.cnt[k]) {
             const float lg = __log2f(fabsf(r4[k]));
-            l2 += (double)sp.cnt[k] * (double)lg;
+            l2 = __fma_rn(sp.cnt_d[k], (double)lg, l2);
             if (guard) {
                 const float t = __uint2float_rn(sp.cnt[k]) * lg;
                 bpos += fmaxf(t, 0.0f);
@@ -535,7 +545,7 @@ __device__ __forceinline__ float fast_finish(const SeqPlan &sp, int esum, int em
             }
         }
     }
-    const float l = (float)(l2 * (0.6931471805599453 / (double)sp.accum));
+    const float l = (float)(l2 * sp.ln2_over_accum);
     const bool bad = (emin == 0) || !is_finite(v) || !is_finite(l);
     if (guard) {
         // |A| = -(esum + log2 mant) >= 0; 1.001: the float arithmetic above must not land just under a binade
@@ -563,10 +573,23 @@ __device__ __forceinline__ void exponent_fast2(const SeqPlan &sp, float xa, floa
     };
 
     if constexpr (P > 0) {
+        // Multiplier pair of a symbol: the four candidate pairs go to this thread's column of a small
+        // shared array once per evaluation and come back with ONE LDS.64 per use at a warp-uniform row
+        // offset -- the plan is decoded per evaluation, and a compare-and-branch select cost ~10
+        // instructions per position of the period (profiles/r02_render_fast_1080p.md).  Only the
+        // owning thread touches its column: no synchronisation.
+        __shared__ f32x2 symtab[4][kSymTabThreads];
+        const uint32_t tb = (uint32_t)__cvta_generic_to_shared(&symtab[0][threadIdx.x]);
+        constexpr uint32_t kRow = kSymTabThreads * (uint32_t)sizeof(f32x2);
+        sts_b64(tb, pack2(xa, xb));
+        sts_b64(tb + kRow, pack2(ya, yb));
+        sts_b64(tb + 2 * kRow, pack2(za, zb));
+        sts_b64(tb + 3 * kRow, pack2(d, d));
+        auto rsel = [&](uint32_t s) { return lds_b64(tb + s * kRow); };
         f32x2 r[P];
 #pragma unroll
-        for (int k = 0; k < P; k++) r[k] = rpair(sp.rot[k]);
-        for (uint32_t n = 0; n < sp.settle_head; n++) settle_step(rpair(sp.sym[n]));
+        for (int k = 0; k < P; k++) r[k] = rsel(sp.rot[k]);
+        for (uint32_t n = 0; n < sp.settle_head; n++) settle_step(rsel(sp.sym[n]));
 #pragma unroll 1
         for (uint32_t i = 0; i < sp.settle_periods; i++) {
 #pragma unroll
@@ -597,7 +620,7 @@ __device__ __forceinline__ void exponent_fast2(const SeqPlan &sp, float xa, floa
         }
 #pragma unroll 1
         for (uint32_t n = 0; n < sp.accum_tail; n++) {
-            acc.step(rpair(sp.rot[n]), w, two, one);
+            acc.step(rsel(sp.rot[n]), w, two, one);
             if ((n & 7) == 7) acc.renorm();
         }
     } else if (sp.table_stride != 0) {
@@ -636,7 +659,7 @@ __device__ __forceinline__ void exponent_fast2(const SeqPlan &sp, float xa, floa
         if (acc.emin0 == 0 && sp.redo) la = fast_redo(sp, xa, ya, za, d);
         if (acc.emin1 == 0 && sp.redo) lb = fast_redo(sp, xb, yb, zb, d);
     }
-    const float zero = __fdiv_rn(0.0f, __uint2float_rn(sp.accum));
+    const float zero = sp.accum ? 0.0f : quiet_nan();   // 0 / accum
     if (vsa == -0.5f) la = zero;   // w == -0.5 <=> v == 0.5 after settling (kernel.cu:138)
     if (vsb == -0.5f) lb = zero;
 }

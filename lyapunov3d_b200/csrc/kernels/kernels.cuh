@@ -168,6 +168,7 @@ struct RenderArgs {
 };
 
 constexpr int kRenderThreads = 128;
+static_assert(kRenderThreads <= kSymTabThreads, "exponent_fast2 keeps one shared-memory column per thread");
 
 // Work item k of a rank -> pixel.  Returns false for the padding of ragged edge tiles.
 __device__ __forceinline__ bool item_to_pixel(const RenderArgs &a, unsigned long long k, uint32_t &x, uint32_t &y)
