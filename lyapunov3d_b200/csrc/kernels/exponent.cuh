@@ -292,7 +292,7 @@ struct Accum<kFast> {
 
 // -------------------------------------------------------------------- driver
 // Out-of-line, rarely taken: the guaranteed-safe evaluation of one sample (defined below).
-static __device__ __noinline__ float fast_redo(const SeqPlan &sp, float x, float y, float z, float d);
+static __device__ __noinline__ float fast_redo(const SeqPlan &sp, float x, float y, float z, float d, uint32_t strip_entry = 4);
 
 template <int P>
 struct PeriodUnroll {
@@ -404,9 +404,11 @@ __device__ __forceinline__ float exponent(const SeqPlan &sp, float x, float y, f
     return l;
 }
 
-static __device__ __noinline__ float fast_redo(const SeqPlan &sp, float x, float y, float z, float d)
+// `strip_entry`: as for exponent() -- the safe loop of a generic-period launch reads the multipliers from the
+// calling thread's own strip of the shared-memory table, whose width the calling kernel fixed.
+static __device__ __noinline__ float fast_redo(const SeqPlan &sp, float x, float y, float z, float d, uint32_t strip_entry)
 {
-    return exponent<kFast, 0>(sp, x, y, z, d);
+    return exponent<kFast, 0>(sp, x, y, z, d, strip_entry);
 }
 
 // ------------------------------------------------- two samples per lane (packed f32x2)
@@ -636,10 +638,23 @@ __device__ __forceinline__ void exponent_fast2(const SeqPlan &sp, float xa, floa
 #pragma unroll 1
         for (uint32_t i = 0; i < sp.settle_periods; i++) table_span<8>(T, sp.len, [&](uint32_t a) { settle_step(lds_b64(a)); }, [] {});
         unpack2(w, vsa, vsb);
+        // 16-step blocks closed by the three-instruction fold (same cadence class as the unrolled periods:
+        // an underflow shows as a zero exponent field and sends the sample to the safe loop below)
+        auto span16 = [&](uint32_t addr, uint32_t count) {
 #pragma unroll 1
-        for (uint32_t i = 0; i < sp.accum_periods; i++)
-            table_span<8>(T, sp.len, [&](uint32_t a) { acc.step(lds_b64(a), w, two, one); }, [&] { acc.renorm(); });
-        table_span<8>(T, sp.accum_tail, [&](uint32_t a) { acc.step(lds_b64(a), w, two, one); }, [&] { acc.renorm(); });
+            for (uint32_t n = count >> 4; n; --n, addr += 16 * 8) {
+#pragma unroll
+                for (int j = 0; j < 15; ++j) acc.step(lds_b64(addr + j * 8), w, two, one);
+                acc.step_abs(lds_b64(addr + 15 * 8), w, two, one);
+                acc.renorm_pos();
+            }
+#pragma unroll 1
+            for (uint32_t n = count & 15u; n; --n, addr += 8) acc.step(lds_b64(addr), w, two, one);
+            acc.renorm();
+        };
+#pragma unroll 1
+        for (uint32_t i = 0; i < sp.accum_periods; i++) span16(T, sp.len);
+        span16(T, sp.accum_tail);
     } else {
         RunCursor cur{0, 0};
         run_steps(sp, cur, sp.settle, rpair, settle_step, [] {});
@@ -653,11 +668,11 @@ __device__ __forceinline__ void exponent_fast2(const SeqPlan &sp, float xa, floa
     unpack2(w, wa, wb);
     la = fast_finish(sp, acc.esum0, acc.emin0, pa, xa, ya, za, d, wa, ga);
     lb = fast_finish(sp, acc.esum1, acc.emin1, pb, xb, yb, zb, d, wb, gb);
-    if constexpr (P > 0) {
-        // zero derivative or (with the 20-step folds) a possible underflow: ask the safe loop
+    if (P > 0 || sp.table_stride != 0) {
+        // zero derivative or (with the 16/20-step folds) a possible underflow: ask the safe loop
         // (its guard stays infinite: a hybrid caller leaves such a sample to the parity evaluator)
-        if (acc.emin0 == 0 && sp.redo) la = fast_redo(sp, xa, ya, za, d);
-        if (acc.emin1 == 0 && sp.redo) lb = fast_redo(sp, xb, yb, zb, d);
+        if (acc.emin0 == 0 && sp.redo) la = fast_redo(sp, xa, ya, za, d, 8);
+        if (acc.emin1 == 0 && sp.redo) lb = fast_redo(sp, xb, yb, zb, d, 8);
     }
     const float zero = sp.accum ? 0.0f : quiet_nan();   // 0 / accum
     if (vsa == -0.5f) la = zero;   // w == -0.5 <=> v == 0.5 after settling (kernel.cu:138)
