@@ -375,8 +375,14 @@ int render_impl(lyap_rgba *d_rgba, lyap_point *d_points, const lyap_cam *cam, co
             int per_sm = host ? march_blocks_per_sm_host(P, a.plan) : march_blocks_per_sm_exact(P, a.plan);
             if (per_sm <= 0) { e = cudaErrorLaunchOutOfResources; break; }
             long want_warps = g_render_warps_per_sm.load();
-            if (want_warps > 0 && (want_warps * 32 + kRenderThreads - 1) / kRenderThreads < per_sm)
-                per_sm = (int)((want_warps * 32 + kRenderThreads - 1) / kRenderThreads);
+            if (want_warps > 0) {
+                if ((want_warps * 32 + kRenderThreads - 1) / kRenderThreads < per_sm)
+                    per_sm = (int)((want_warps * 32 + kRenderThreads - 1) / kRenderThreads);
+            } else {
+                // small shards: fewer ray slots, more rays per slot (see the single-launch rule below)
+                const unsigned long long slots = 2ull * sc->sm_count * per_sm * kRenderThreads;
+                if (per_sm > 2 && a.n_items < 6ull * slots) per_sm -= 1;
+            }
             unsigned long long grid = (unsigned long long)sc->sm_count * per_sm;
             const unsigned long long max_useful = (a.n_items + 2 * kRenderThreads - 1) / (2 * kRenderThreads);
             if (grid > max_useful) grid = max_useful;
@@ -418,6 +424,11 @@ int render_impl(lyap_rgba *d_rgba, lyap_point *d_points, const lyap_cam *cam, co
         // lane pays (measured on 1/4 and 1/8 of a 1080p frame: 74.5 -> 72.6 ms, 43.4 -> 41.6 ms).
         const unsigned long long lanes = (unsigned long long)sc->sm_count * per_sm * kRenderThreads;
         if (per_sm > 3 && a.n_items < 9ull * lanes) per_sm -= 1;
+    } else {
+        // the two-ray kernel holds 2 x 128 rays per block: the same trade at three blocks per SM (measured on 1/8
+        // and 1/4 of a 1080p frame, profiles/r02_shard_warps.log: 27.8 -> 26.5 ms, 45.5 -> 44.8 ms)
+        const unsigned long long slots = 2ull * sc->sm_count * per_sm * kRenderThreads;
+        if (per_sm > 2 && a.n_items < 6ull * slots) per_sm -= 1;
     }
     unsigned long long grid = (unsigned long long)sc->sm_count * per_sm;
     const unsigned long long max_useful = (a.n_items + kRenderThreads - 1) / kRenderThreads;
