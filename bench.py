@@ -562,7 +562,10 @@ def main():
         except Exception as exc:          # a missing checker must not take the headline down
             ref_cuda = {"unavailable": repr(exc)}
 
-    n_kernels = 2 if (args.mode.startswith("hybrid") and prm.jitter == 0.0) else 1
+    # kernels of ours per step: the render kernel (march + refine in hybrid mode) and, for a frame, the seven
+    # small launches that order its tile queue (tile_key_kernel + CUB radix sort: histogram, scan, 4 passes;
+    # ~60 us together -- profiles/r02_launches_bench_exact.csv)
+    n_kernels = (2 if (args.mode.startswith("hybrid") and prm.jitter == 0.0) else 1) + (7 if run.frame else 0)
     line = {
         "metric": "lyapunov_giga_iters_per_s", "value": value, "unit": "Giter/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,

@@ -72,7 +72,11 @@ const char *lyap_error_string(int code);
  * "emulate_ref_nvcc_normals" (test knob: reproduce the normals the reference's CUDA
  * build produces under nvcc 12.9, where ls[] aliases lyap4d's abcd[]),
  * "hybrid_guard_batch" (parked lanes per warp that trigger a parity pass; 0 = default = 1),
- * "hybrid_guard_percent" (test knob: guard band width in % of the derived bound).
+ * "hybrid_guard_percent" (test knob: guard band width in % of the derived bound),
+ * "tail_compaction" (1 = default: repack the last rays of a frame launch into fewer warps),
+ * "tile_order" (1 = default: a frame launch queues its tiles by descending chord length of
+ * the centre ray, an upper bound of the march length, so that the rays started last are
+ * short; 0 = image order.  The output does not depend on either).
  * The knobs are process-global and read at launch time: set them before launching from
  * several threads, not concurrently with launches. */
 int lyap_set_option(const char *key, long value);

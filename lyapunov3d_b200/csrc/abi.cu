@@ -31,6 +31,7 @@ std::atomic<long> g_render_warps_per_sm{0};   // 0 = default
 std::atomic<long> g_bake_blocks_per_sm{0};    // 0 = occupancy maximum
 std::atomic<long> g_fast_redo{1};             // debug knob: 0 disables the safe re-evaluation in fast mode
 std::atomic<long> g_nvcc_normal_quirk{0};     // test knob: emulate the reference CUDA build's aliased normals
+std::atomic<long> g_tile_order{1};            // frame queue in chord-descending tile order (0 = image order, for measurements)
 std::atomic<long> g_tail_compaction{1};       // render_kernel's tail protocol (0 = off, for measurements)
 std::atomic<long> g_guard_batch{0};           // hybrid mode: parked lanes per warp that trigger a parity pass (0 = default)
 std::atomic<long> g_guard_scale{100};         // hybrid mode: guard band width in percent of the derived bound (test knob)
@@ -228,6 +229,7 @@ int lyap_set_option(const char *key, long value)
     else if (!strcmp(key, "emulate_ref_nvcc_normals")) g_nvcc_normal_quirk = value;
     else if (!strcmp(key, "fast_redo")) g_fast_redo = value;
     else if (!strcmp(key, "tail_compaction")) g_tail_compaction = value;
+    else if (!strcmp(key, "tile_order")) g_tile_order = value;
     else if (!strcmp(key, "hybrid_guard_batch")) g_guard_batch = value;
     else if (!strcmp(key, "hybrid_guard_percent")) g_guard_scale = value;
     else return LYAP_ERR_BAD_ARGUMENT;
@@ -341,6 +343,19 @@ int render_impl(lyap_rgba *d_rgba, lyap_point *d_points, const lyap_cam *cam, co
     cudaStream_t s = (cudaStream_t)stream;
     a.queue = sc->counters + (sc->next.fetch_add(1) % kCounterRing);
     if ((e = cudaMemsetAsync(a.queue, 0, sizeof(unsigned long long), s)) != cudaSuccess) return (int)e;
+    // Queue order: tiles whose rays can be long first (kernels.cuh: RenderArgs::tile_order).  The compact
+    // (work-order) output of the gather path keeps image order: lyap_scatter_tiles places by it.
+    a.tile_order = nullptr;
+    struct StreamScratch {
+        void *p = nullptr;
+        cudaStream_t s;
+        ~StreamScratch() { if (p) cudaFreeAsync(p, s); }   // after everything queued on s below
+    } order_mem;
+    order_mem.s = s;
+    if (!compact && a.n_tiles > 1 && g_tile_order.load()) {
+        if ((e = cudaMallocAsync(&order_mem.p, tile_order_scratch_bytes(a.n_tiles), s)) != cudaSuccess) return (int)e;
+        if ((e = launch_tile_order(a, order_mem.p, &a.tile_order, s)) != cudaSuccess) return (int)e;
+    }
     a.worklist = nullptr;
     a.work_count = nullptr;
     a.safe_bits = nullptr;

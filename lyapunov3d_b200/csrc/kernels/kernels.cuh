@@ -165,6 +165,12 @@ struct RenderArgs {
     unsigned long long *skipped;       // optional: += skipped samples
     uint32_t sm_count;                 // SMs of the device (informational)
     uint32_t tail_compaction;          // 0 switches the tail protocol of render_kernel off
+    // Optional permutation of the image's tiles (n_tiles entries): queue position -> tile.  The launch ends with
+    // its longest ray, so the queue hands out the tiles whose rays CAN be long first and the provably short ones
+    // last: tiles sorted by the length of the centre ray's chord through the cube, which bounds its march from
+    // above (misc.cu: launch_tile_order).  Ranks interleave over queue positions, so every rank computes the
+    // same permutation and takes positions rank, rank + world, ...  Null = image order.
+    const uint32_t *tile_order;
 };
 
 constexpr int kRenderThreads = 128;
@@ -175,10 +181,12 @@ __device__ __forceinline__ bool item_to_pixel(const RenderArgs &a, unsigned long
 {
     const uint32_t tt = a.tile * a.tile;
     const uint32_t m = (uint32_t)(k / tt), p = (uint32_t)(k % tt);
-    const uint32_t j = m * a.world + a.rank;
+    const uint32_t pos = m * a.world + a.rank;
+    if (pos >= a.n_tiles) { x = y = 0; return false; }
+    const uint32_t j = a.tile_order ? __ldg(a.tile_order + pos) : pos;
     x = (j % a.tiles_x) * a.tile + p % a.tile;
     y = (j / a.tiles_x) * a.tile + p / a.tile;
-    return j < a.n_tiles && x < a.width && y < a.height;
+    return x < a.width && y < a.height;
 }
 
 template <class A>

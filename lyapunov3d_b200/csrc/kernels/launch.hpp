@@ -63,6 +63,10 @@ cudaError_t launch_march_host(int P, const RenderArgs &a, unsigned grid, cudaStr
 int march_blocks_per_sm_exact(int P, const SeqPlan &plan);
 int march_blocks_per_sm_host(int P, const SeqPlan &plan);
 
+// Tile permutation of a frame launch (RenderArgs::tile_order): `scratch` of tile_order_scratch_bytes(n_tiles)
+// device bytes, used on stream s; *order points into it and is valid for work queued on s afterwards.
+size_t tile_order_scratch_bytes(uint32_t n_tiles);
+cudaError_t launch_tile_order(const RenderArgs &a, void *scratch, const uint32_t **order, cudaStream_t s);
 cudaError_t launch_shade(int mode, const ShadeArgs &a, unsigned grid, cudaStream_t s);
 cudaError_t launch_scatter(const ScatterArgs &a, unsigned grid, cudaStream_t s);
 cudaError_t launch_assist_build(const AssistBuildArgs &a, unsigned grid, cudaStream_t s);

@@ -2,9 +2,81 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "launch.hpp"
 
 namespace lyap {
+
+// ---- tile order of a frame launch -----------------------------------------------------------
+// Key of a tile: the chord of its centre ray through the cube in march steps' own unit (t1 - t0 of
+// ray_begin), an upper bound on how long that ray can march with a fixed step (stepMethod 2); with
+// stepMethod 1 every ray takes `depth` steps, so all hitting tiles get the same key and keep image
+// order.  Tiles whose centre ray misses the cube get 0 and go last.  A stable descending radix sort:
+// same keys on every rank (same arithmetic on the same inputs), same permutation.
+struct TileKeyArgs {
+    lyap_cam cam;
+    lyap_params prm;
+    uint32_t width, height, tile, tiles_x, n_tiles;
+    float *keys;
+    uint32_t *ids;
+};
+
+__global__ void __launch_bounds__(256) tile_key_kernel(const __grid_constant__ TileKeyArgs a)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= a.n_tiles) return;
+    const uint32_t px = min((j % a.tiles_x) * a.tile + a.tile / 2, a.width - 1);
+    const uint32_t py = min((j / a.tiles_x) * a.tile + a.tile / 2, a.height - 1);
+    MarchState st;
+    float key = 0.0f;
+    if (ray_begin<ArithDev>(st, px, py, a.cam, a.prm)) {
+        key = a.prm.stepMethod == 1 ? 1.0f : st.t1 - st.t;
+        if (!(key > 0.0f)) key = 0.0f;   // NaN or a degenerate chord
+    }
+    a.keys[j] = key;
+    a.ids[j] = j;
+}
+
+static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+static size_t tile_sort_temp_bytes(uint32_t n_tiles)
+{
+    size_t temp = 0;
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, temp, (const float *)nullptr, (float *)nullptr, (const uint32_t *)nullptr,
+                                              (uint32_t *)nullptr, (int)n_tiles);
+    return temp;
+}
+
+size_t tile_order_scratch_bytes(uint32_t n_tiles)
+{
+    return 4 * align256((size_t)n_tiles * 4) + align256(tile_sort_temp_bytes(n_tiles));
+}
+
+cudaError_t launch_tile_order(const RenderArgs &r, void *scratch, const uint32_t **order, cudaStream_t s)
+{
+    const size_t arr = align256((size_t)r.n_tiles * 4);
+    unsigned char *base = static_cast<unsigned char *>(scratch);
+    float *keys_in = reinterpret_cast<float *>(base), *keys_out = reinterpret_cast<float *>(base + arr);
+    uint32_t *ids_in = reinterpret_cast<uint32_t *>(base + 2 * arr), *ids_out = reinterpret_cast<uint32_t *>(base + 3 * arr);
+    TileKeyArgs a;
+    a.cam = r.cam;
+    a.prm = r.prm;
+    a.width = r.width;
+    a.height = r.height;
+    a.tile = r.tile;
+    a.tiles_x = r.tiles_x;
+    a.n_tiles = r.n_tiles;
+    a.keys = keys_in;
+    a.ids = ids_in;
+    tile_key_kernel<<<(r.n_tiles + 255) / 256, 256, 0, s>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    size_t temp = tile_sort_temp_bytes(r.n_tiles);
+    e = cub::DeviceRadixSort::SortPairsDescending(base + 4 * arr, temp, keys_in, keys_out, ids_in, ids_out, (int)r.n_tiles, 0, 32, s);
+    *order = ids_out;
+    return e;
+}
 
 cudaError_t launch_shade(int mode, const ShadeArgs &a, unsigned grid, cudaStream_t s)
 {

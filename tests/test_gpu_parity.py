@@ -683,6 +683,46 @@ def test_tail_compaction_does_not_change_a_single_byte(scene, mode):
         assert int(out[0][2].item()) == int(out[1][2].item()), (mode, w, h)
 
 
+@pytest.mark.parametrize("mode", ["exact", "fast", "hybrid"])
+def test_tile_order_does_not_change_a_single_byte(scene, mode):
+    """A frame launch queues its tiles by descending chord length of the centre ray (the rays started last
+    are then provably short).  The order of the queue cannot change any pixel: frames, records and evaluation
+    counts are identical with image order -- whole frames, assembled shards, stepMethod 1 (all keys equal), a wide
+    camera (tiles that miss the cube) and an image of a single tile."""
+    prm, cam, lights, n, seq = scene
+    p = clone(prm)
+    if mode == "hybrid":
+        p.jitter = 0.0
+    p1 = clone(p)
+    p1.stepMethod = 1
+    p1.depth = 160
+    wide = clone(cam)
+    lp.campath_frame(0, 120, wide)      # the orbit's first camera, opened up as the golden wide_32 frame is:
+    wide.M = 1.2                        # many rays miss the cube
+    cases = [(p, cam, 200, 120), (p1, cam, 96, 64), (p, wide, 160, 96), (p, cam, 8, 8)]
+    for (pp, cc, w, h) in cases:
+        c = clone(cc)
+        lp.scene_cam_recalculate(c, w, h, 1)
+        out = []
+        for order in (1, 0):
+            api.set_option("tile_order", order)
+            try:
+                out.append(lp.render(c, pp, seq, lights, n, w, h, mode=mode))
+                if (w, h) == (200, 120):
+                    # the ranks of a sharded frame take queue positions rank, rank + world, ... of the SAME
+                    # permutation: their shards (different tiles under the two orders) assemble to the frame
+                    rgba = torch.zeros_like(out[-1][0])
+                    pts = torch.zeros_like(out[-1][1])
+                    ev = 0
+                    for r in range(3):
+                        ev += int(lp.render(c, pp, seq, lights, n, w, h, mode=mode, tile=8, rank=r, world=3, rgba=rgba, points=pts)[2].item())
+                    assert torch.equal(rgba, out[-1][0]) and torch.equal(pts, out[-1][1]) and ev == int(out[-1][2].item()), (mode, order)
+            finally:
+                api.set_option("tile_order", 1)
+        assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1]), (mode, w, h)
+        assert int(out[0][2].item()) == int(out[1][2].item()), (mode, w, h)
+
+
 def test_host_buffer_api_equals_device_api(scene):
     prm, cam, lights, n, seq = scene
     c = clone(cam)
