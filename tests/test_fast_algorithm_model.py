@@ -96,6 +96,47 @@ def test_twenty_step_folds_cannot_lose_a_typical_orbit():
     assert (2.0 ** 120) * (2.0 ** -12) ** 20 > 2.0 ** -126    # ... and when it does not
 
 
+def test_three_instruction_fold_keeps_the_same_books():
+    """Round 2's cheaper fold (exponent.cuh: AccumFast2::step_abs + renorm_pos + close): the step before a fold
+    multiplies |prod| * |q|, so the fold reads a value without a sign bit and needs no masks:
+        esum += bits >> 23          (raw exponent; nfold biases are taken off once at the end)
+        emin  = min(emin, bits)     (raw bits; a zero exponent field <=> emin < 2^23)
+        prod  = (bits & mantissa) | bias
+    Modelled here step for step against the original fold (mask the sign, subtract the bias each time, track the
+    minimum exponent field) on random products of either sign, including zeros, denormals and underflows:
+    same exponent sums, same mantissas, same zero-field verdict."""
+    rng = np.random.default_rng(11)
+    n, bias = 4096, 120
+    seed = np.uint32((127 + bias) << 23)
+    prod_a = np.full(n, 2.0 ** bias, F)
+    prod_b = prod_a.copy()
+    esum_a = np.zeros(n, np.int64); emin_a = np.full(n, 255, np.int64)                    # original form
+    esum_b = np.zeros(n, np.int64); emin_b = np.full(n, 0x7FFFFFFF, np.int64); nfold = 0  # three-instruction form
+    with np.errstate(all="ignore"):
+        for fold in range(40):
+            for k in range(20):
+                # factors |q| <= 1 of either sign; a few exact zeros and tiny ones so that some lanes underflow
+                q = (rng.uniform(-1, 1, n) * np.where(rng.random(n) < 0.02, 2.0 ** -24, 1.0)).astype(F)
+                q[rng.random(n) < 0.0005] = F(0)
+                prod_a = (prod_a * q).astype(F)
+                prod_b = (np.abs(prod_b) * np.abs(q)).astype(F) if k == 19 else (prod_b * q).astype(F)
+            bits = np.abs(prod_a).view(np.uint32)                  # original: drop the sign, then shift and mask
+            e = (bits >> 23).astype(np.int64) & 0xFF
+            esum_a += e - (127 + bias)
+            emin_a = np.minimum(emin_a, e)
+            prod_a = ((bits & np.uint32(0x007FFFFF)) | seed).view(F)
+            raw = prod_b.view(np.uint32)                           # new: no sign bit by construction
+            assert (raw >> 31 == 0).all()
+            esum_b += (raw >> 23).astype(np.int64)
+            emin_b = np.minimum(emin_b, raw.astype(np.int64))
+            nfold += 1
+            prod_b = ((raw & np.uint32(0x007FFFFF)) | seed).view(F)
+            assert (prod_a.view(np.uint32) == prod_b.view(np.uint32)).all(), fold
+    esum_b -= nfold * (127 + bias)
+    assert (esum_a == esum_b).all()
+    assert ((emin_a == 0) == (emin_b >> 23 == 0)).all() and (emin_a == 0).any() and (emin_a != 0).any()
+
+
 def test_fma_trajectory_equals_the_references_double_tail_except_for_rare_double_roundings():
     """The reference steps the orbit as v' = (float)((double)(r*v) * (1.0 - (double)v)) (kernel.cu:135,143:
     a float product, then a double tail); every mode here steps it as p = r*v; v' = fma(-p, v, p).
