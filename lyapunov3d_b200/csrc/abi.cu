@@ -352,7 +352,7 @@ int render_impl(lyap_rgba *d_rgba, lyap_point *d_points, const lyap_cam *cam, co
         ~StreamScratch() { if (p) cudaFreeAsync(p, s); }   // after everything queued on s below
     } order_mem;
     order_mem.s = s;
-    if (!compact && a.n_tiles > 1 && g_tile_order.load()) {
+    if (!compact && a.n_tiles > 1 && a.n_tiles <= (1u << 30) && g_tile_order.load()) {   // (the sort counts in int)
         if ((e = cudaMallocAsync(&order_mem.p, tile_order_scratch_bytes(a.n_tiles), s)) != cudaSuccess) return (int)e;
         if ((e = launch_tile_order(a, order_mem.p, &a.tile_order, s)) != cudaSuccess) return (int)e;
     }
