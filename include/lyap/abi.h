@@ -73,6 +73,9 @@ const char *lyap_error_string(int code);
  * build produces under nvcc 12.9, where ls[] aliases lyap4d's abcd[]),
  * "hybrid_guard_batch" (parked lanes per warp that trigger a parity pass; 0 = default = 1),
  * "hybrid_guard_percent" (test knob: guard band width in % of the derived bound),
+ * "fast_redo" (1 = default: a FAST-mode sample whose exponent fold saw a zero exponent field
+ * -- a zero derivative or an underflow between two folds -- is evaluated again by the
+ * guaranteed-safe loop; 0 reports NaN for it at once, for measurements),
  * "tail_compaction" (1 = default: repack the last rays of a frame launch into fewer warps),
  * "tile_order" (1 = default: a frame launch queues its tiles by descending chord length of
  * the centre ray, an upper bound of the march length, so that the rays started last are

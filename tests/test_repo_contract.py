@@ -38,3 +38,14 @@ def test_every_cuda_source_is_in_the_build():
         cu |= {os.path.relpath(os.path.join(d, f), _build.CSRC) for f in files if f.endswith(".cu")}
     assert cu == set(_build.CU), cu ^ set(_build.CU)
     assert "arch=compute_100a,code=sm_100a" in " ".join(_build.NVCC_FLAGS) and "-lineinfo" in _build.NVCC_FLAGS
+
+
+def test_every_option_knob_is_documented_in_the_header():
+    """lyap_set_option's keys (csrc/abi.cu) all appear in include/lyap/abi.h's description of the knobs."""
+    import re
+    src = open(os.path.join(ROOT, "lyapunov3d_b200", "csrc", "abi.cu")).read()
+    hdr = open(os.path.join(ROOT, "include", "lyap", "abi.h")).read()
+    keys = re.findall(r'strcmp\(key, "([a-z_0-9]+)"\)', src)
+    assert len(keys) >= 10
+    missing = [k for k in keys if '"%s"' % k not in hdr]
+    assert not missing, missing
